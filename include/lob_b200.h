@@ -1,0 +1,228 @@
+/*
+ * lob_b200.h -- C ABI of liblob_b200.so: sm_100a kernels for the batched Krylov hot path of
+ * cornellius-gp/linear_operator (mBCG + stochastic Lanczos quadrature + pivoted-Cholesky preconditioner +
+ * structured matmuls).  The reference is pure Python on PyTorch and has no FFI of its own; each entry point below
+ * names the reference code (path:line relative to /root/reference/linear_operator) whose arithmetic it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions (every call):
+ *   - all pointers are DEVICE pointers unless the parameter name starts with host_; the caller owns every buffer
+ *     (inputs, outputs, workspaces); the library never allocates device memory and keeps no pointer after return;
+ *   - tensors are dense row-major; vectors are (B, N, C) with C fastest, B = product of the batch dimensions;
+ *   - dtype: LOB_F32 or LOB_F64; `stream` is a cudaStream_t passed as void*;
+ *   - calls are stream-ordered and never synchronise the host unless the name ends in _sync;
+ *   - return value: LOB_OK or a negative error code, message via lob_last_error() (thread local).
+ *     Numerical conditions (NaNs, no convergence) are NOT errors: they are reported through device status words
+ *     which the Python host turns into the reference's RuntimeError / NumericalWarning.
+ */
+#ifndef LOB_B200_H
+#define LOB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOB_F32 0
+#define LOB_F64 1
+
+#define LOB_OK 0
+#define LOB_ERR_ARG (-1)
+#define LOB_ERR_CUDA (-2)
+#define LOB_ERR_UNSUPPORTED (-3)
+
+int lob_version(void);
+const char* lob_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
+int64_t lob_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Modified batched CG (utils/linear_cg.py:98-359).  The host drives the iteration (the operator's _matmul and the
+ * preconditioner are closures on the reference's API), every per-iteration vector/scalar update is fused here.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t B, N, C;          /* batch, operator size, right-hand-side columns                         */
+  int32_t dtype;            /* LOB_F32 / LOB_F64                                                     */
+  int32_t n_tridiag;        /* S: tridiagonals are recovered for the first S columns (0 = none)      */
+  int32_t n_tridiag_iter;   /* T = min(max_tridiag_iter, N)            (linear_cg.py:171)            */
+  int32_t max_iter;         /* settings.max_cg_iterations               (linear_cg.py:139-140)       */
+  int32_t n_iter;           /* iterations the loop may run              (linear_cg.py:170)           */
+  int32_t has_precond;      /* 1: z = M^-1 r is supplied by the caller each iteration                */
+  double tolerance;         /* settings.cg_tolerance                    (linear_cg.py:150-151)       */
+  double eps;               /* 1e-10 safe-division threshold            (linear_cg.py:103,172)       */
+  double stop_updating_after; /* 1e-10 per-column freeze threshold      (linear_cg.py:104,205,300)   */
+} lob_cg_params;
+
+/* control words kept in the workspace and copied out by lob_cg_poll_sync */
+typedef struct {
+  int32_t stop;               /* loop has ended (tolerance reached or NaN)            */
+  int32_t tolerance_reached;  /* linear_cg.py:307                                      */
+  int32_t iterations;         /* completed iterations (k+1)                            */
+  int32_t update_tridiag;     /* linear_cg.py:238,326-327                              */
+  int32_t last_tridiag_iter;  /* linear_cg.py:239,329                                  */
+  int32_t nan_detected;       /* linear_cg.py:199-200                                  */
+  int32_t all_converged_at_start; /* linear_cg.py:207                                  */
+  int32_t reserved;
+  double residual_norm_mean;  /* for the NumericalWarning text (linear_cg.py:337-347)  */
+} lob_cg_status;
+
+size_t lob_cg_workspace_bytes(const lob_cg_params* p);
+
+/* linear_cg.py:177-183: column norms of rhs (zero columns flagged, norm := 1), rhs_n = rhs / norm,
+ * x = x0 / norm (x0 may be NULL -> x = 0).  Also resets the control words and zero-fills t_mat (may be NULL,
+ * shape (S, B, T, T)). */
+int lob_cg_setup(const lob_cg_params* p, void* ws, const void* rhs, const void* x0, void* rhs_n, void* x,
+                 void* t_mat, void* stream);
+
+/* linear_cg.py:186-208: r = rhs_n - ax0 (ax0 = A x0, may be NULL when x0 was NULL: r = rhs_n), NaN check,
+ * residual norms, has_converged. */
+int lob_cg_residual_init(const lob_cg_params* p, void* ws, const void* rhs_n, const void* ax0, void* r, void* stream);
+
+/* linear_cg.py:213-215: rz = sum z*r, p = z.  z may alias r (no preconditioner). */
+int lob_cg_direction_init(const lob_cg_params* p, void* ws, const void* r, const void* z, void* pvec, void* stream);
+
+/* linear_cg.py:250-264 (+ :31 x update): alpha = rz / <p,Ap> with the eps rule and the converged mask,
+ * r -= alpha Ap, x += alpha p; also accumulates <r,r> for the residual norm.
+ * pap_partials: optional (B, n_parts, C) partial sums of p*Ap in double precision written by a fused matmul
+ * (lob_dense_matmul); NULL -> computed here. */
+int lob_cg_step_xr(const lob_cg_params* p, void* ws, int32_t k, const void* ap, const void* pvec, void* x, void* r,
+                   const double* pap_partials, int32_t n_parts, void* stream);
+
+/* linear_cg.py:31-46 + :298-332: beta = <r,z>_new / <r,z>_old (eps rule), p = z + beta p, residual norm / converged
+ * flags, stop test, tridiagonal update.  z NULL -> z = r.  t_mat (S,B,T,T) may be NULL when n_tridiag == 0. */
+int lob_cg_step_p(const lob_cg_params* p, void* ws, int32_t k, const void* z, const void* r, void* pvec, void* t_mat,
+                  void* stream);
+
+/* copies the control words to host memory and synchronises the stream */
+int lob_cg_poll_sync(const lob_cg_params* p, void* ws, lob_cg_status* host_status, void* stream);
+
+/* linear_cg.py:335: x *= rhs_norm */
+int lob_cg_finish(const lob_cg_params* p, void* ws, void* x, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense operator matmul: Y = A X (+ d (.) X), A (B|1, M, K) row-major with leading dimension lda,
+ * X (B, K, C), Y (B, M, C).   dense_linear_operator.py:60-64 + added_diag_linear_operator.py:72-76.
+ * a_batch_stride / d_batch_stride in elements (0 broadcasts over the batch); d may be NULL; d_stride is the element
+ * stride inside one diagonal (0 for a constant diagonal stored as one value per batch element).
+ * If dots != NULL (requires M == K) it receives (B, lob_dense_matmul_parts(M), C) double partial sums of X*Y over
+ * row tiles: the <p, A p> reduction of linear_cg.py:250-251 fused into the matmul epilogue.
+ * ---------------------------------------------------------------------------------------------------------- */
+int32_t lob_dense_matmul_parts(int64_t M);
+int lob_dense_matmul(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A, int64_t lda,
+                     int64_t a_batch_stride, const void* X, void* Y, const void* d, int64_t d_batch_stride,
+                     int64_t d_stride, double* dots, void* stream);
+
+/* Out (B, I, J) = P^T Q with P (B, N, I), Q (B, N, J) row-major: reductions over the long dimension N
+ * (Q^T r of added_diag_linear_operator.py:137, L^T L of the preconditioner build, U^T (D^-1 b) of
+ * low_rank_root_added_diag_linear_operator.py:77).  Accumulates in double; deterministic two-stage reduction.
+ * ws must hold lob_tn_matmul_workspace_bytes(). out_dtype selects the type of Out (LOB_F64 allowed for f32 in). */
+size_t lob_tn_matmul_workspace_bytes(int64_t B, int64_t N, int64_t I, int64_t J);
+int lob_tn_matmul(int32_t dtype, int32_t out_dtype, int64_t B, int64_t N, int64_t I, int64_t J, const void* P,
+                  int64_t p_batch_stride, const void* Q, int64_t q_batch_stride, void* out, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Pivoted-Cholesky preconditioner of AddedDiagLinearOperator
+ * ---------------------------------------------------------------------------------------------------------- */
+/* functions/_pivoted_cholesky.py:13-105 for a dense operator A (B, N, N): greedy diagonal-pivoted partial Cholesky.
+ * Lt (B, rank, N) zero-filled on entry receives row m = step m (the reference's internal layout, :36-42);
+ * perm (B, N) int64; m_out (device int32) = number of steps actually taken (common to the batch, :57).
+ * ws: lob_pivchol_workspace_bytes().  Row sources other than dense: see the kron / toeplitz variants. */
+size_t lob_pivchol_workspace_bytes(int64_t B, int64_t N, int32_t rank);
+int lob_pivchol_dense(int32_t dtype, int64_t B, int64_t N, int32_t rank, double error_tol, const void* A, int64_t lda,
+                      int64_t a_batch_stride, void* Lt, int64_t* perm, int32_t* m_out, void* ws, void* stream);
+/* kronecker_product_linear_operator.py:198-216 row source: up to 4 factors, factor f is (B|1, n_f, n_f) */
+int lob_pivchol_kron(int32_t dtype, int64_t B, int32_t n_factors, const int64_t* host_sizes,
+                     const void* const* host_factors, const int64_t* host_batch_strides, int32_t rank,
+                     double error_tol, void* Lt, int64_t* perm, int32_t* m_out, void* ws, void* stream);
+/* toeplitz_linear_operator.py:38-40 row source: T[i,j] = col[|i-j|], col (B|1, N) */
+int lob_pivchol_toeplitz(int32_t dtype, int64_t B, int64_t N, const void* col, int64_t col_batch_stride, int32_t rank,
+                         double error_tol, void* Lt, int64_t* perm, int32_t* m_out, void* ws, void* stream);
+
+/* (B, R, N) -> (B, N, m) keeping the first m rows: the `L[..., :m, :].mT.contiguous()` of _pivoted_cholesky.py:104 */
+int lob_transpose_rows(int32_t dtype, int64_t B, int64_t R, int64_t N, int64_t m, const void* Lt, void* L,
+                       void* stream);
+
+/* added_diag_linear_operator.py:144-184 restated through the Gram matrix (R^T R = L^T D^-1 L + I, resp. L^T L + s I):
+ * given G (B, k, k) in double (from lob_tn_matmul), adds the diagonal term, factors it in-SM and returns
+ * Rinv (B, k, k) in `dtype` (upper triangular inverse: Q = L Rinv) and logdet_r (B) = 2 sum log R_ii.
+ * The diagonal added to G is sigma2[b * sigma2_stride] when sigma2 != NULL, else add_identity_scale.
+ * info (B) != 0 flags a non-positive pivot.  ws: B*k*k doubles.  k <= 160. */
+int lob_precond_factor(int32_t dtype, int64_t B, int32_t k, const double* G, double add_identity_scale,
+                       const void* sigma2, int64_t sigma2_stride, void* rinv, void* logdet_r, int32_t* info, void* ws,
+                       void* stream);
+
+/* fused elementwise pieces of precondition_closure (added_diag_linear_operator.py:135-140):
+ * z = (r - w) * inv_sigma2[b]  (constant diagonal)   or   z = r / d - w   (general diagonal), w = Q (Q^T r). */
+int lob_precond_combine(int32_t dtype, int64_t B, int64_t N, int64_t C, const void* r, const void* w, const void* d,
+                        int64_t d_batch_stride, int64_t d_stride, int32_t constant_diag, void* z, void* stream);
+
+/* rows scaled: out[b,n,:] = in[b,n,:] * f(d[b,n]),  mode 0: *d, 1: /d, 2: *sqrt(d), 3: /sqrt(d)
+ * (D^-1/2 L of added_diag_linear_operator.py:176-178, D^-1 b of low_rank_root_added_diag_linear_operator.py:77) */
+int lob_scale_rows(int32_t dtype, int64_t B, int64_t N, int64_t C, const void* in, const void* d,
+                   int64_t d_batch_stride, int64_t d_stride, int32_t mode, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Probe vectors, column reductions
+ * ---------------------------------------------------------------------------------------------------------- */
+/* functions/_inv_quad_logdet.py:107-110 + psd_sum_linear_operator.py:15-18 + diag_linear_operator.py:273-277:
+ * z (B,N,S) = z_root (B,N,S, may be NULL) + sqrt(d[b,n]) * eps_diag (S,B,N) (d NULL -> 1); then column norms and
+ * normalisation.  probes (B,N,S) and norms (B,1,S) are outputs.  ws: lob_colred_workspace_bytes(B,N,S). */
+size_t lob_colred_workspace_bytes(int64_t B, int64_t N, int64_t C);
+int lob_probe_assemble(int32_t dtype, int64_t B, int64_t N, int64_t S, const void* z_root, const void* eps_diag,
+                       const void* d, int64_t d_batch_stride, int64_t d_stride, void* probes, void* norms, void* ws,
+                       void* stream);
+
+/* out[b, j] = sum_n U[b, n, u_off + j] * V[b, n, v_off + j], j < R  (inv_quad = (solves[..., S:] * rhs).sum(-2),
+ * functions/_inv_quad_logdet.py:151-153).  U is (B,N,Cu), V is (B,N,Cv). */
+int lob_col_dots(int32_t dtype, int64_t B, int64_t N, int64_t R, const void* U, int64_t Cu, int64_t u_off,
+                 const void* V, int64_t Cv, int64_t v_off, void* out, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stochastic Lanczos quadrature (utils/lanczos.py:167-189 + utils/stochastic_lq.py:45-82)
+ * ---------------------------------------------------------------------------------------------------------- */
+/* t_mat (S, B, T, T) symmetric tridiagonal.  evals (S,B,T) ascending with negative eigenvalues replaced by 1 and
+ * their eigenvector columns zeroed; evecs (S,B,T,T) may be NULL (first rows only are needed for the quadrature);
+ * logdet (B) = (n / S) sum_j sum_i V_j[0,i]^2 log(lambda_ji) may be NULL.  All arithmetic in double on device
+ * (the reference ships T<32 problems to CPU LAPACK, lanczos.py:179-180).  ws: lob_tridiag_workspace_bytes(). */
+size_t lob_tridiag_workspace_bytes(int64_t S, int64_t B, int32_t T, int32_t want_evecs);
+int lob_tridiag_eigh_slq(int32_t dtype, int64_t S, int64_t B, int32_t T, int64_t n, const void* t_mat, void* evals,
+                         void* evecs, void* logdet, int32_t* info, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Structured matmuls
+ * ---------------------------------------------------------------------------------------------------------- */
+/* kronecker_product_linear_operator.py:34-45: one mode product  Y[b, q, i, c] = sum_j K[b, i, j] X[b, j, q, c]
+ * for X viewed as (B, n, Q, C) and Y as (B, Q, n, C): the bmm and the transposing copy of the reference fused. */
+int lob_kron_mode_matmul(int32_t dtype, int64_t B, int64_t n, int64_t Q, int64_t C, const void* K,
+                         int64_t k_batch_stride, const void* X, void* Y, void* stream);
+
+/* utils/toeplitz.py:131-149 with a length-L (>= 2N-1) real circulant embedding; the FFTs themselves are cuFFT.
+ * pad: xt (B, C, L) = [X^T, 0];  embed: c (B, L) = [col, 0.., rev(col[1:])];
+ * mul: Fy = Fx * Fc (complex, (B,C,L/2+1) x (B,L/2+1));  unpad: Y (B,N,C) = scale * yt[..., :N]^T (+ d (.) X). */
+int lob_toeplitz_pad(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* X, void* xt, void* stream);
+int lob_toeplitz_embed(int32_t dtype, int64_t B, int64_t N, int64_t L, const void* col, int64_t col_batch_stride,
+                       void* c, void* stream);
+int lob_toeplitz_mul(int32_t dtype, int64_t B, int64_t C, int64_t H, const void* fc, int64_t fc_batch_stride, void* fx,
+                     void* stream);
+int lob_toeplitz_unpad(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* yt, double scale,
+                       const void* X, const void* d, int64_t d_batch_stride, int64_t d_stride, void* Y, void* stream);
+
+/* generic batched small-K product  Y (B, M, C) = A (B|1, M, K) X (B, K, C): Q t, L eps, U w
+ * (added_diag_linear_operator.py:137, _linear_operator.py:2784-2791, low_rank_root_added_diag_...py:83).
+ * Same kernel as lob_dense_matmul without the fused epilogues; beta_y: Y = A X + beta_y * Y. */
+int lob_matmul_nn(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A, int64_t lda,
+                  int64_t a_batch_stride, const void* X, int64_t x_batch_stride, void* Y, double beta_y, void* stream);
+
+/* Woodbury pieces of low_rank_root_added_diag_linear_operator.py:36-47,62-101: in-SM Cholesky solve of the k x k
+ * capacitance system for C right-hand sides: W (B,k,C) <- cap^-1 W, cap = I + G (G (B|1,k,k) double);
+ * logdet_cap (B) = 2 sum log diag chol(cap). */
+size_t lob_cap_solve_workspace_bytes(int64_t B, int32_t k, int64_t C);
+int lob_cap_solve(int32_t dtype, int64_t B, int32_t k, int64_t C, const double* G, int64_t g_batch_stride, void* W,
+                  void* logdet_cap, int32_t* info, void* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOB_B200_H */

@@ -1,0 +1,469 @@
+"""Typed torch-tensor wrappers over the C ABI (``include/lob_b200.h``).  Shape checks live here; arithmetic does not.
+
+Every function takes CUDA tensors, flattens the leading batch dimensions to one ``B`` and launches on the current
+stream of the tensors' device.  Nothing here falls back to PyTorch math.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, dt, ptr, require_cuda, stream, workspace
+
+
+def _flat3(t: torch.Tensor) -> torch.Tensor:
+    """(*batch, R, C) -> contiguous (B, R, C)"""
+    t = t.contiguous()
+    return t.reshape(-1, t.shape[-2], t.shape[-1])
+
+
+def _numel(shape) -> int:
+    return int(math.prod(shape)) if len(shape) else 1
+
+
+def _diag_args(d: Optional[torch.Tensor], batch_shape, n: int):
+    """Normalises a diagonal given as (*batch, N) or (*batch, 1) (constant) to (tensor, batch_stride, elem_stride).
+    A stride-0 expanded diagonal (ConstantDiagLinearOperator._diag, diag_linear_operator.py:346-350) is passed through
+    without materialising it."""
+    if d is None:
+        return None, 0, 0
+    B = _numel(batch_shape)
+    if d.shape[-1] == 1 or (d.dim() >= 1 and d.stride(-1) == 0):
+        base = d[..., :1]
+        base = base.expand(*batch_shape, 1).reshape(B, 1).contiguous() if base.numel() != B else base.reshape(B, 1).contiguous()
+        return base, 1, 0
+    full = d.expand(*batch_shape, n).reshape(B, n).contiguous()
+    return full, n, 1
+
+
+# ------------------------------------------------------------------------------------------------------------
+# matmuls
+# ------------------------------------------------------------------------------------------------------------
+def dense_matmul(A: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = None, want_dots: bool = False):
+    """Y = A X (+ d (.) X); A (*ba, M, K), X (*b, K, C).  Returns Y or (Y, dots, n_parts)."""
+    require_cuda(A, X, d)
+    lib = _lib.load()
+    M, K = A.shape[-2:]
+    if X.shape[-2] != K:
+        raise RuntimeError(f"Size mismatch: operator is {tuple(A.shape)}, right-hand side is {tuple(X.shape)}")
+    batch_shape = torch.broadcast_shapes(A.shape[:-2], X.shape[:-2])
+    B = _numel(batch_shape)
+    C = X.shape[-1]
+    Xf = _flat3(X.expand(*batch_shape, K, C))
+    if _numel(A.shape[:-2]) == 1:
+        Af = A.reshape(1, M, K)
+        if Af.stride(-1) != 1 or Af.stride(-2) < K:
+            Af = Af.contiguous()
+        a_bs = 0
+    else:
+        Af = _flat3(A.expand(*batch_shape, M, K))
+        a_bs = Af.stride(0)
+    lda = Af.stride(-2)
+    Y = torch.empty(B, M, C, dtype=X.dtype, device=X.device)
+    dd, d_bs, d_st = _diag_args(d, batch_shape, M)
+    dots = None
+    n_parts = int(lib.lob_dense_matmul_parts(M))
+    if want_dots:
+        dots = torch.empty(B, n_parts, C, dtype=torch.float64, device=X.device)
+    check(
+        lib.lob_dense_matmul(dt(X), B, M, K, C, ptr(Af), lda, a_bs, ptr(Xf), ptr(Y), ptr(dd), d_bs, d_st, ptr(dots),
+                             stream(X)),
+        "lob_dense_matmul",
+    )
+    Y = Y.reshape(*batch_shape, M, C)
+    if want_dots:
+        return Y, dots, n_parts
+    return Y
+
+
+def matmul_nn(A: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+    """Y = A X for small-K products (Q t, L eps, U w).  A (*ba, M, K), X (*bx, K, C), batches broadcast."""
+    require_cuda(A, X)
+    lib = _lib.load()
+    M, K = A.shape[-2:]
+    C = X.shape[-1]
+    if X.shape[-2] != K:
+        raise RuntimeError(f"Size mismatch: {tuple(A.shape)} @ {tuple(X.shape)}")
+    batch_shape = torch.broadcast_shapes(A.shape[:-2], X.shape[:-2])
+    B = _numel(batch_shape)
+    if _numel(A.shape[:-2]) == 1:
+        Af, a_bs = A.reshape(1, M, K).contiguous(), 0
+    else:
+        Af = _flat3(A.expand(*batch_shape, M, K))
+        a_bs = M * K
+    if _numel(X.shape[:-2]) == 1:
+        Xf, x_bs = X.reshape(1, K, C).contiguous(), 0
+    else:
+        Xf = _flat3(X.expand(*batch_shape, K, C))
+        x_bs = K * C
+    Y = torch.empty(B, M, C, dtype=X.dtype, device=X.device)
+    check(lib.lob_matmul_nn(dt(X), B, M, K, C, ptr(Af), K, a_bs, ptr(Xf), x_bs, ptr(Y), 0.0, stream(X)), "lob_matmul_nn")
+    return Y.reshape(*batch_shape, M, C)
+
+
+def tn_matmul(P: torch.Tensor, Q: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Out = P^T Q, reduction over the long (row) dimension.  P (*bp, N, I), Q (*bq, N, J)."""
+    require_cuda(P, Q)
+    lib = _lib.load()
+    N, I = P.shape[-2:]
+    J = Q.shape[-1]
+    if Q.shape[-2] != N:
+        raise RuntimeError(f"Size mismatch: {tuple(P.shape)}^T @ {tuple(Q.shape)}")
+    batch_shape = torch.broadcast_shapes(P.shape[:-2], Q.shape[:-2])
+    B = _numel(batch_shape)
+    if _numel(P.shape[:-2]) == 1:
+        Pf, p_bs = P.reshape(1, N, I).contiguous(), 0
+    else:
+        Pf, p_bs = _flat3(P.expand(*batch_shape, N, I)), N * I
+    if _numel(Q.shape[:-2]) == 1:
+        Qf, q_bs = Q.reshape(1, N, J).contiguous(), 0
+    else:
+        Qf, q_bs = _flat3(Q.expand(*batch_shape, N, J)), N * J
+    out_dtype = out_dtype or P.dtype
+    out = torch.empty(B, I, J, dtype=out_dtype, device=P.device)
+    ws = workspace(lib.lob_tn_matmul_workspace_bytes(B, N, I, J), P.device)
+    check(
+        lib.lob_tn_matmul(dt(P), _lib._DT[out_dtype], B, N, I, J, ptr(Pf), p_bs, ptr(Qf), q_bs, ptr(out), ptr(ws),
+                          stream(P)),
+        "lob_tn_matmul",
+    )
+    return out.reshape(*batch_shape, I, J)
+
+
+def scale_rows(X: torch.Tensor, d: torch.Tensor, mode: str) -> torch.Tensor:
+    """rows of X (*b, N, C) scaled by f(d (*b, N) or (*b, 1)); mode in {"mul","div","mul_sqrt","div_sqrt"}"""
+    require_cuda(X, d)
+    lib = _lib.load()
+    modes = {"mul": 0, "div": 1, "mul_sqrt": 2, "div_sqrt": 3}
+    batch_shape = torch.broadcast_shapes(X.shape[:-2], d.shape[:-1])
+    N, C = X.shape[-2:]
+    Xf = _flat3(X.expand(*batch_shape, N, C))
+    dd, d_bs, d_st = _diag_args(d, batch_shape, N)
+    out = torch.empty_like(Xf)
+    check(lib.lob_scale_rows(dt(X), Xf.shape[0], N, C, ptr(Xf), ptr(dd), d_bs, d_st, modes[mode], ptr(out), stream(X)),
+          "lob_scale_rows")
+    return out.reshape(*batch_shape, N, C)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# pivoted Cholesky + preconditioner
+# ------------------------------------------------------------------------------------------------------------
+def _pivchol_finish(lib, Lt, perm, m_out, batch_shape, N, rankmax):
+    m = int(m_out.item())  # the factor's width is data dependent: one host read, like the reference's per-step sync
+    B = Lt.shape[0]
+    L = torch.empty(B, N, m, dtype=Lt.dtype, device=Lt.device)
+    check(lib.lob_transpose_rows(dt(Lt), B, rankmax, N, m, ptr(Lt), ptr(L), stream(Lt)), "lob_transpose_rows")
+    return L.reshape(*batch_shape, N, m), perm.reshape(*batch_shape, N)
+
+
+def pivoted_cholesky_dense(A: torch.Tensor, rank: int, tol: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    require_cuda(A)
+    lib = _lib.load()
+    batch_shape = A.shape[:-2]
+    N = A.shape[-1]
+    Af = _flat3(A)
+    B = Af.shape[0]
+    rankmax = min(int(rank), N)
+    Lt = torch.zeros(B, rankmax, N, dtype=A.dtype, device=A.device)
+    perm = torch.empty(B, N, dtype=torch.int64, device=A.device)
+    m_out = torch.zeros(1, dtype=torch.int32, device=A.device)
+    ws = workspace(lib.lob_pivchol_workspace_bytes(B, N, rankmax), A.device)
+    check(
+        lib.lob_pivchol_dense(dt(A), B, N, rankmax, float(tol), ptr(Af), N, N * N, ptr(Lt), ptr(perm), ptr(m_out),
+                              ptr(ws), stream(A)),
+        "lob_pivchol_dense",
+    )
+    return _pivchol_finish(lib, Lt, perm, m_out, batch_shape, N, rankmax)
+
+
+def pivoted_cholesky_kron(factors: Sequence[torch.Tensor], batch_shape, rank: int, tol: float):
+    require_cuda(*factors)
+    lib = _lib.load()
+    if not 1 <= len(factors) <= 4:
+        raise _lib.LobError("Kronecker pivoted Cholesky supports 1..4 factors")
+    B = _numel(batch_shape)
+    sizes = [int(f.shape[-1]) for f in factors]
+    N = int(math.prod(sizes))
+    flat, strides = [], []
+    for f in factors:
+        if _numel(f.shape[:-2]) == 1:
+            flat.append(f.reshape(1, *f.shape[-2:]).contiguous())
+            strides.append(0)
+        else:
+            ff = _flat3(f.expand(*batch_shape, *f.shape[-2:]))
+            flat.append(ff)
+            strides.append(ff.shape[-1] * ff.shape[-2])
+    ref = flat[0]
+    rankmax = min(int(rank), N)
+    Lt = torch.zeros(B, rankmax, N, dtype=ref.dtype, device=ref.device)
+    perm = torch.empty(B, N, dtype=torch.int64, device=ref.device)
+    m_out = torch.zeros(1, dtype=torch.int32, device=ref.device)
+    ws = workspace(lib.lob_pivchol_workspace_bytes(B, N, rankmax), ref.device)
+    nf = len(flat)
+    c_sizes = (ctypes.c_int64 * nf)(*sizes)
+    c_ptrs = (ctypes.c_void_p * nf)(*[f.data_ptr() for f in flat])
+    c_strides = (ctypes.c_int64 * nf)(*strides)
+    check(
+        lib.lob_pivchol_kron(dt(ref), B, nf, c_sizes, c_ptrs, c_strides, rankmax, float(tol), ptr(Lt), ptr(perm),
+                             ptr(m_out), ptr(ws), stream(ref)),
+        "lob_pivchol_kron",
+    )
+    return _pivchol_finish(lib, Lt, perm, m_out, batch_shape, N, rankmax)
+
+
+def pivoted_cholesky_toeplitz(col: torch.Tensor, rank: int, tol: float):
+    require_cuda(col)
+    lib = _lib.load()
+    batch_shape = col.shape[:-1]
+    N = col.shape[-1]
+    cf = col.contiguous().reshape(-1, N)
+    B = cf.shape[0]
+    rankmax = min(int(rank), N)
+    Lt = torch.zeros(B, rankmax, N, dtype=col.dtype, device=col.device)
+    perm = torch.empty(B, N, dtype=torch.int64, device=col.device)
+    m_out = torch.zeros(1, dtype=torch.int32, device=col.device)
+    ws = workspace(lib.lob_pivchol_workspace_bytes(B, N, rankmax), col.device)
+    check(
+        lib.lob_pivchol_toeplitz(dt(col), B, N, ptr(cf), N, rankmax, float(tol), ptr(Lt), ptr(perm), ptr(m_out),
+                                 ptr(ws), stream(col)),
+        "lob_pivchol_toeplitz",
+    )
+    return _pivchol_finish(lib, Lt, perm, m_out, batch_shape, N, rankmax)
+
+
+class AddedDiagPreconditioner:
+    """M = L L^T + D from a pivoted-Cholesky factor (added_diag_linear_operator.py:144-184).
+
+    Holds Q (*b, N, k) with M^-1 v = (v - Q Q^T v)/s (constant diagonal) or v/d - Q Q^T v (general diagonal) and
+    logdet(M).  Built through the k x k Gram matrix in double (see csrc/precond.cu)."""
+
+    def __init__(self, L: torch.Tensor, diag: torch.Tensor, constant: bool):
+        require_cuda(L, diag)
+        lib = _lib.load()
+        self.batch_shape = L.shape[:-2]
+        N, k = L.shape[-2:]
+        self.N, self.k, self.constant = N, k, constant
+        B = _numel(self.batch_shape)
+        dev, dty = L.device, L.dtype
+        if constant:
+            self.noise = diag[..., :1].expand(*self.batch_shape, 1).reshape(B, 1).contiguous()  # sigma^2 per batch elt
+            Ls = L
+        else:
+            self.noise = diag.expand(*self.batch_shape, N).reshape(B, N).contiguous()
+            Ls = scale_rows(L, self.noise.reshape(*self.batch_shape, N), "div_sqrt")  # D^-1/2 L (:176-178)
+        G = tn_matmul(Ls, Ls, out_dtype=torch.float64).reshape(B, k, k)
+        rinv = torch.empty(B, k, k, dtype=dty, device=dev)
+        logdet_r = torch.empty(B, dtype=dty, device=dev)
+        info = torch.zeros(B, dtype=torch.int32, device=dev)
+        ws = workspace(B * k * k * 8, dev)
+        check(
+            lib.lob_precond_factor(dt(L), B, k, ptr(G), 1.0, ptr(self.noise) if constant else None, 1, ptr(rinv),
+                                   ptr(logdet_r), ptr(info), ptr(ws), stream(L)),
+            "lob_precond_factor",
+        )
+        Q = matmul_nn(Ls.reshape(B, N, k), rinv)  # Q1 = L R^-1
+        if constant:
+            self.Q = Q
+            # logdet M = 2 sum log|R_ii| + (N - k) log s   (:170-172); tiny (B,) op on the control path
+            self.logdet = logdet_r + (N - k) * self.noise[:, 0].log()
+        else:
+            self.Q = scale_rows(Q, self.noise, "div_sqrt")  # D^-1/2 Q1 (:179)
+            self.logdet = logdet_r + self.noise.log().sum(-1)  # :182-183
+        self.logdet = self.logdet.reshape(self.batch_shape) if len(self.batch_shape) else self.logdet.squeeze()
+        self._info = info
+
+    def __call__(self, v: torch.Tensor) -> torch.Tensor:
+        """precondition_closure (added_diag_linear_operator.py:135-140)"""
+        require_cuda(v)
+        lib = _lib.load()
+        squeeze = v.dim() == 1
+        if squeeze:
+            v = v.unsqueeze(-1)
+        batch_shape = torch.broadcast_shapes(self.batch_shape, v.shape[:-2])
+        N, C = v.shape[-2:]
+        vf = _flat3(v.expand(*batch_shape, N, C))
+        B = vf.shape[0]
+        Qf = self.Q if B == self.Q.shape[0] else self.Q.reshape(*self.batch_shape, N, self.k).expand(
+            *batch_shape, N, self.k).reshape(B, N, self.k)
+        t = tn_matmul(Qf, vf)
+        w = matmul_nn(Qf, t)
+        z = torch.empty_like(vf)
+        noise = self.noise if B == self.noise.shape[0] else self.noise.reshape(*self.batch_shape, -1).expand(
+            *batch_shape, self.noise.shape[-1]).reshape(B, -1).contiguous()
+        check(
+            lib.lob_precond_combine(dt(v), B, N, C, ptr(vf), ptr(w), ptr(noise), noise.shape[-1],
+                                    0 if self.constant else 1, 1 if self.constant else 0, ptr(z), stream(v)),
+            "lob_precond_combine",
+        )
+        z = z.reshape(*batch_shape, N, C)
+        return z.squeeze(-1) if squeeze else z
+
+
+# ------------------------------------------------------------------------------------------------------------
+# probes, column reductions, quadrature
+# ------------------------------------------------------------------------------------------------------------
+def probe_assemble(z_root: Optional[torch.Tensor], eps_diag: torch.Tensor, d: Optional[torch.Tensor]):
+    """probes (*b, N, S), norms (*b, 1, S) from z_root (*b, N, S) and eps_diag (S, *b, N)
+    (functions/_inv_quad_logdet.py:107-110)."""
+    require_cuda(z_root, eps_diag, d)
+    lib = _lib.load()
+    S = eps_diag.shape[0]
+    batch_shape = eps_diag.shape[1:-1]
+    N = eps_diag.shape[-1]
+    B = _numel(batch_shape)
+    ef = eps_diag.contiguous().reshape(S, B, N)
+    zf = None if z_root is None else _flat3(z_root)
+    dd, d_bs, d_st = _diag_args(d, batch_shape, N)
+    probes = torch.empty(B, N, S, dtype=ef.dtype, device=ef.device)
+    norms = torch.empty(B, 1, S, dtype=ef.dtype, device=ef.device)
+    ws = workspace(lib.lob_colred_workspace_bytes(B, N, S), ef.device)
+    check(
+        lib.lob_probe_assemble(dt(ef), B, N, S, ptr(zf), ptr(ef), ptr(dd), d_bs, d_st, ptr(probes), ptr(norms), ptr(ws),
+                               stream(ef)),
+        "lob_probe_assemble",
+    )
+    return probes.reshape(*batch_shape, N, S), norms.reshape(*batch_shape, 1, S)
+
+
+def col_dots(U: torch.Tensor, u_off: int, V: torch.Tensor, v_off: int, R: int) -> torch.Tensor:
+    """out (*b, R) = sum_n U[..., n, u_off + j] V[..., n, v_off + j]"""
+    require_cuda(U, V)
+    lib = _lib.load()
+    batch_shape = U.shape[:-2]
+    Uf, Vf = _flat3(U), _flat3(V)
+    B, N, Cu = Uf.shape
+    Cv = Vf.shape[-1]
+    out = torch.empty(B, R, dtype=U.dtype, device=U.device)
+    ws = workspace(lib.lob_colred_workspace_bytes(B, N, R), U.device)
+    check(lib.lob_col_dots(dt(U), B, N, R, ptr(Uf), Cu, u_off, ptr(Vf), Cv, v_off, ptr(out), ptr(ws), stream(U)),
+          "lob_col_dots")
+    return out.reshape(*batch_shape, R)
+
+
+def tridiag_eigh_slq(t_mat: torch.Tensor, n: int, want_evals=False, want_evecs=False, want_logdet=True):
+    """t_mat (S, *b, T, T).  Returns dict with the requested of evals (S,*b,T), evecs (S,*b,T,T), logdet (*b)."""
+    require_cuda(t_mat)
+    lib = _lib.load()
+    S = t_mat.shape[0]
+    batch_shape = t_mat.shape[1:-2]
+    T = t_mat.shape[-1]
+    B = _numel(batch_shape)
+    tf = t_mat.contiguous()
+    dev, dty = t_mat.device, t_mat.dtype
+    evals = torch.empty(S, B, T, dtype=dty, device=dev) if want_evals else None
+    evecs = torch.empty(S, B, T, T, dtype=dty, device=dev) if want_evecs else None
+    logdet = torch.empty(B, dtype=dty, device=dev) if want_logdet else None
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = workspace(lib.lob_tridiag_workspace_bytes(S, B, T, 1 if want_evecs else 0), dev)
+    check(
+        lib.lob_tridiag_eigh_slq(dt(t_mat), S, B, T, int(n), ptr(tf), ptr(evals), ptr(evecs), ptr(logdet), ptr(info),
+                                 ptr(ws), stream(t_mat)),
+        "lob_tridiag_eigh_slq",
+    )
+    out = {}
+    if want_evals:
+        out["evals"] = evals.reshape(S, *batch_shape, T)
+    if want_evecs:
+        out["evecs"] = evecs.reshape(S, *batch_shape, T, T)
+    if want_logdet:
+        out["logdet"] = logdet.reshape(batch_shape)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# structured matmuls
+# ------------------------------------------------------------------------------------------------------------
+def kron_matmul(factors: Sequence[torch.Tensor], X: torch.Tensor) -> torch.Tensor:
+    """(K1 (x) K2 (x) ...) X as one fused mode product per factor (kronecker_product_linear_operator.py:34-45)."""
+    require_cuda(X, *factors)
+    lib = _lib.load()
+    batch_shape = torch.broadcast_shapes(X.shape[:-2], *[f.shape[:-2] for f in factors])
+    B = _numel(batch_shape)
+    Ntot, C = X.shape[-2:]
+    cur = _flat3(X.expand(*batch_shape, Ntot, C))
+    if cur.data_ptr() == X.data_ptr():
+        pass  # never written: the first mode product writes to a fresh buffer
+    for f in factors:
+        n = f.shape[-1]
+        if f.shape[-2] != n:
+            raise _lib.LobError("Kronecker matmul kernel expects square factors")
+        Q = Ntot // n
+        if _numel(f.shape[:-2]) == 1:
+            ff, k_bs = f.reshape(1, n, n).contiguous(), 0
+        else:
+            ff, k_bs = _flat3(f.expand(*batch_shape, n, n)), n * n
+        out = torch.empty_like(cur)
+        check(lib.lob_kron_mode_matmul(dt(X), B, n, Q, C, ptr(ff), k_bs, ptr(cur), ptr(out), stream(X)),
+              "lob_kron_mode_matmul")
+        cur = out
+    return cur.reshape(*batch_shape, Ntot, C)
+
+
+def _next_pow2(n: int) -> int:
+    return 1 << (int(n) - 1).bit_length()
+
+
+def toeplitz_embed_fft(col: torch.Tensor):
+    """FFT of the circulant embedding of a symmetric Toeplitz column: returns (fc (B, L/2+1) complex, L)."""
+    require_cuda(col)
+    lib = _lib.load()
+    N = col.shape[-1]
+    L = _next_pow2(2 * N)
+    cf = col.contiguous().reshape(-1, N)
+    B = cf.shape[0]
+    c = torch.empty(B, L, dtype=col.dtype, device=col.device)
+    check(lib.lob_toeplitz_embed(dt(col), B, N, L, ptr(cf), N, ptr(c), stream(col)), "lob_toeplitz_embed")
+    return torch.fft.rfft(c), L  # cuFFT R2C
+
+
+def toeplitz_matmul(col: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = None, fc_cache=None):
+    """Symmetric Toeplitz matmul through a length-L (power of two >= 2N) real circulant embedding
+    (utils/toeplitz.py:131-149 uses length 2N-1 complex FFTs; any L >= 2N-1 gives the same product).
+    Optionally fuses + d (.) X."""
+    require_cuda(col, X, d)
+    lib = _lib.load()
+    N, C = X.shape[-2:]
+    batch_shape = torch.broadcast_shapes(col.shape[:-1], X.shape[:-2])
+    B = _numel(batch_shape)
+    Xf = _flat3(X.expand(*batch_shape, N, C))
+    if fc_cache is None:
+        fc_cache = toeplitz_embed_fft(col)
+    fc, L = fc_cache
+    fc_bs = 0 if fc.shape[0] == 1 and B > 1 else fc.shape[-1]
+    xt = torch.empty(B, C, L, dtype=X.dtype, device=X.device)
+    check(lib.lob_toeplitz_pad(dt(X), B, N, C, L, ptr(Xf), ptr(xt), stream(X)), "lob_toeplitz_pad")
+    fx = torch.fft.rfft(xt)  # cuFFT R2C, batched over (B, C)
+    H = fx.shape[-1]
+    check(lib.lob_toeplitz_mul(dt(X), B, C, H, ptr(fc), fc_bs, ptr(fx), stream(X)), "lob_toeplitz_mul")
+    yt = torch.fft.irfft(fx, n=L)  # cuFFT C2R (normalised by 1/L)
+    Y = torch.empty(B, N, C, dtype=X.dtype, device=X.device)
+    dd, d_bs, d_st = _diag_args(d, batch_shape, N)
+    check(
+        lib.lob_toeplitz_unpad(dt(X), B, N, C, L, ptr(yt), 1.0, ptr(Xf), ptr(dd), d_bs, d_st, ptr(Y), stream(X)),
+        "lob_toeplitz_unpad",
+    )
+    return Y.reshape(*batch_shape, N, C)
+
+
+def cap_solve(G: torch.Tensor, W: torch.Tensor):
+    """W <- (I + G)^-1 W, logdet(I + G).  G (*bg, k, k) float64, W (*b, k, C)."""
+    require_cuda(G, W)
+    lib = _lib.load()
+    batch_shape = W.shape[:-2]
+    k, C = W.shape[-2:]
+    Wf = _flat3(W).clone()
+    B = Wf.shape[0]
+    if _numel(G.shape[:-2]) == 1:
+        Gf, g_bs = G.reshape(1, k, k).contiguous(), 0
+    else:
+        Gf, g_bs = _flat3(G.expand(*batch_shape, k, k)), k * k
+    logdet = torch.empty(B, dtype=W.dtype, device=W.device)
+    info = torch.zeros(B, dtype=torch.int32, device=W.device)
+    ws = workspace(lib.lob_cap_solve_workspace_bytes(B, k, C), W.device)
+    check(lib.lob_cap_solve(dt(W), B, k, C, ptr(Gf), g_bs, ptr(Wf), ptr(logdet), ptr(info), ptr(ws), stream(W)),
+          "lob_cap_solve")
+    return Wf.reshape(*batch_shape, k, C), logdet.reshape(batch_shape), info

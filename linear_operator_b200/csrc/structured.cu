@@ -1,0 +1,300 @@
+// structured.cu -- structured-operator matmul pieces and the low-rank Woodbury capacitance solve.
+//   Kronecker : kronecker_product_linear_operator.py:34-45   (one fused mode product per factor)
+//   Toeplitz  : utils/toeplitz.py:131-149                    (pad / embed / pointwise-multiply / unpad around cuFFT)
+//   Low rank  : low_rank_root_added_diag_linear_operator.py:36-47,62-101
+#include "common.cuh"
+#include "simt_tile.cuh"
+
+namespace lob {
+
+// Y[b, q, i, c] = sum_j K[b, i, j] X[b, j, q, c].   X is (B, n, Q*C) row-major, so this is the GEMM
+// (n x n)(n x QC) with the output tile scattered as (Q, n, C): the reference's bmm + transposing copy in one pass.
+template <typename T, int RN>
+__global__ void __launch_bounds__(256)
+k_kron_mode(int64_t n, int64_t Q, int64_t C, const T* __restrict__ K, int64_t k_bs, const T* __restrict__ X,
+            T* __restrict__ Y) {
+  constexpr int TK = TileK<T>::value;
+  constexpr int CP = 8 * RN;
+  __shared__ __align__(16) T As[TK * LDA_S];
+  __shared__ __align__(16) T Bs[TK * CP];
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  const int64_t b = blockIdx.y;
+  const int64_t QC = Q * C;
+  const int64_t f0 = (int64_t)blockIdx.x * CP;
+  const int64_t m0 = (int64_t)blockIdx.z * TM;
+  const T* Kb = K + b * k_bs;
+  const T* Xb = X + b * n * QC;
+  T* Yb = Y + b * n * QC;
+  const int ncol = (int)min((int64_t)CP, QC - f0);
+  T acc[4][RN];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < RN; ++j) acc[i][j] = (T)0;
+  for (int64_t k0 = 0; k0 < n; k0 += TK) {
+    for (int e = tid; e < TM * TK; e += 256) {
+      const int row = e / TK, kk = e % TK;
+      T v = (T)0;
+      if (m0 + row < n && k0 + kk < n) v = __ldg(Kb + (m0 + row) * n + k0 + kk);
+      As[kk * LDA_S + row] = v;
+    }
+    for (int e = tid; e < TK * CP; e += 256) {
+      const int kk = e / CP, cc = e % CP;
+      T v = (T)0;
+      if (k0 + kk < n && cc < ncol) v = __ldg(Xb + (k0 + kk) * QC + f0 + cc);
+      Bs[e] = v;
+    }
+    __syncthreads();
+    tile_fma<T, T, RN, TK>(As, Bs, CP, ty, tx, acc);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t row = m0 + ty * 4 + i;
+    if (row >= n) continue;
+#pragma unroll
+    for (int j = 0; j < RN; ++j) {
+      const int cc = tx * RN + j;
+      if (cc >= ncol) continue;
+      const int64_t f = f0 + cc, q = f / C, c = f % C;
+      Yb[(q * n + row) * C + c] = acc[i][j];
+    }
+  }
+}
+
+// xt (B, C, L) = [X^T, 0]
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_toeplitz_pad(int64_t N, int64_t C, int64_t L, const T* __restrict__ X, T* __restrict__ xt) {
+  __shared__ T tile[32][33];
+  const int64_t b = blockIdx.z;
+  const int64_t l0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int nl = ty; nl < 32; nl += 8) {
+    const int64_t n = l0 + nl, c = c0 + tx;
+    tile[nl][tx] = (n < N && c < C) ? X[(b * N + n) * C + c] : (T)0;
+  }
+  __syncthreads();
+  for (int cl = ty; cl < 32; cl += 8) {
+    const int64_t c = c0 + cl, l = l0 + tx;
+    if (c < C && l < L) xt[(b * C + c) * L + l] = tile[tx][cl];
+  }
+}
+
+// c (B, L) = [col_0..col_{N-1}, 0, ..., 0, col_{N-1}..col_1]   (utils/toeplitz.py:131-139 with padding in the middle)
+template <typename T>
+__global__ void k_toeplitz_embed(int64_t N, int64_t L, const T* __restrict__ col, int64_t col_bs, T* __restrict__ c,
+                                 int64_t total) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int64_t b = idx / L, l = idx % L;
+  T v = (T)0;
+  if (l < N) v = col[b * col_bs + l];
+  else if (L - l < N) v = col[b * col_bs + (L - l)];
+  c[idx] = v;
+}
+
+// fx[b,c,h] *= fc[b,h]  (complex)
+template <typename T2>
+__global__ void k_toeplitz_mul(int64_t C, int64_t H, const T2* __restrict__ fc, int64_t fc_bs, T2* __restrict__ fx,
+                               int64_t total) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int64_t b = idx / (C * H), h = idx % H;
+  const T2 a = fx[idx], w = fc[b * fc_bs + h];
+  T2 r;
+  r.x = a.x * w.x - a.y * w.y;
+  r.y = a.x * w.y + a.y * w.x;
+  fx[idx] = r;
+}
+
+// Y (B,N,C) = scale * yt[b,c,n] (+ d (.) X)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_toeplitz_unpad(int64_t N, int64_t C, int64_t L, const T* __restrict__ yt, T scale, const T* __restrict__ X,
+                 const T* __restrict__ d, int64_t d_bs, int64_t d_st, T* __restrict__ Y) {
+  __shared__ T tile[32][33];
+  const int64_t b = blockIdx.z;
+  const int64_t n0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int cl = ty; cl < 32; cl += 8) {
+    const int64_t c = c0 + cl, n = n0 + tx;
+    tile[cl][tx] = (c < C && n < N) ? yt[(b * C + c) * L + n] : (T)0;
+  }
+  __syncthreads();
+  for (int nl = ty; nl < 32; nl += 8) {
+    const int64_t n = n0 + nl, c = c0 + tx;
+    if (n < N && c < C) {
+      const int64_t idx = (b * N + n) * C + c;
+      T v = scale * tile[tx][nl];
+      if (d) v += d[b * d_bs + n * d_st] * X[idx];
+      Y[idx] = v;
+    }
+  }
+}
+
+// cap = I + G; W <- cap^-1 W via Cholesky in a double workspace held in global memory (L2 resident), one CTA per
+// batch element.  logdet_cap = 2 sum log diag chol(cap).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_cap_solve(int k, int64_t C, const double* __restrict__ G, int64_t g_bs, T* __restrict__ W, T* __restrict__ logdet,
+            int32_t* __restrict__ info, double* __restrict__ ws) {
+  __shared__ double scratch[32];
+  __shared__ int bad;
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x;
+  double* a = ws + b * ((int64_t)k * k + (int64_t)k * C);
+  double* w = a + (int64_t)k * k;
+  const double* g = G + b * g_bs;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < k * k; e += blockDim.x) a[e] = g[e] + ((e / k) == (e % k) ? 1.0 : 0.0);
+  for (int64_t e = tid; e < (int64_t)k * C; e += blockDim.x) w[e] = (double)W[b * k * C + e];
+  __syncthreads();
+  for (int j = 0; j < k; ++j) {
+    if (tid == 0) {
+      const double p = a[j * k + j];
+      if (!(p > 0.0)) bad = 1;
+      a[j * k + j] = sqrt(p);
+    }
+    __syncthreads();
+    const double djj = a[j * k + j];
+    for (int i = j + 1 + tid; i < k; i += blockDim.x) a[i * k + j] /= djj;
+    __syncthreads();
+    const int rem = k - j - 1;
+    for (int e = tid; e < rem * rem; e += blockDim.x) {
+      const int i = j + 1 + e / rem, m = j + 1 + e % rem;
+      if (m <= i) a[i * k + m] -= a[i * k + j] * a[m * k + j];
+    }
+    __syncthreads();
+  }
+  double acc = 0.0;
+  for (int i = tid; i < k; i += blockDim.x) acc += log(a[i * k + i]);
+  const double ls = block_sum(acc, scratch);
+  if (tid == 0) {
+    logdet[b] = (T)(2.0 * ls);
+    info[b] = bad;
+  }
+  // forward then backward substitution, one thread per right-hand-side column
+  for (int64_t c = tid; c < C; c += blockDim.x) {
+    for (int i = 0; i < k; ++i) {
+      double s = w[i * C + c];
+      for (int m = 0; m < i; ++m) s -= a[i * k + m] * w[m * C + c];
+      w[i * C + c] = s / a[i * k + i];
+    }
+    for (int i = k - 1; i >= 0; --i) {
+      double s = w[i * C + c];
+      for (int m = i + 1; m < k; ++m) s -= a[m * k + i] * w[m * C + c];
+      w[i * C + c] = s / a[i * k + i];
+    }
+    for (int i = 0; i < k; ++i) W[b * k * C + i * C + c] = (T)w[i * C + c];
+  }
+}
+
+}  // namespace lob
+
+namespace lob {
+template <typename T>
+static int launch_kron(int64_t B, int64_t n, int64_t Q, int64_t C, const T* K, int64_t k_bs, const T* X, T* Y,
+                       cudaStream_t st) {
+  const int64_t QC = Q * C;
+  const int rn = pick_rn(QC);
+  dim3 grid((unsigned)cdiv(QC, 8 * rn), (unsigned)B, (unsigned)cdiv(n, TM));
+#define LOB_KR_CASE(R)                                                    \
+  case R:                                                                 \
+    k_kron_mode<T, R><<<grid, 256, 0, st>>>(n, Q, C, K, k_bs, X, Y);      \
+    break;
+  switch (rn) {
+    LOB_KR_CASE(1) LOB_KR_CASE(2) LOB_KR_CASE(3) LOB_KR_CASE(4) LOB_KR_CASE(5) LOB_KR_CASE(6) LOB_KR_CASE(7)
+    LOB_KR_CASE(8)
+  }
+#undef LOB_KR_CASE
+  return check_launch("k_kron_mode");
+}
+}  // namespace lob
+
+using namespace lob;
+
+extern "C" int lob_kron_mode_matmul(int32_t dtype, int64_t B, int64_t n, int64_t Q, int64_t C, const void* K,
+                                    int64_t k_batch_stride, const void* X, void* Y, void* stream) {
+  LOB_REQUIRE(B > 0 && n > 0 && Q > 0 && C > 0, "lob_kron_mode_matmul: sizes must be positive");
+  LOB_REQUIRE(B <= 65535, "lob_kron_mode_matmul: flattened batch > 65535 not supported");
+  LOB_REQUIRE(K && X && Y && X != Y, "lob_kron_mode_matmul: NULL or aliased pointer");
+  LOB_DISPATCH_DTYPE(dtype, {
+    return launch_kron<scalar_t>(B, n, Q, C, (const scalar_t*)K, k_batch_stride, (const scalar_t*)X, (scalar_t*)Y,
+                                 (cudaStream_t)stream);
+  });
+}
+
+extern "C" int lob_toeplitz_pad(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* X, void* xt,
+                                void* stream) {
+  LOB_REQUIRE(B > 0 && N > 0 && C > 0 && L >= N, "lob_toeplitz_pad: bad sizes");
+  LOB_REQUIRE(B <= 65535, "lob_toeplitz_pad: flattened batch > 65535 not supported");
+  LOB_REQUIRE(X && xt, "lob_toeplitz_pad: NULL pointer");
+  dim3 grid((unsigned)cdiv(L, 32), (unsigned)cdiv(C, 32), (unsigned)B);
+  LOB_DISPATCH_DTYPE(dtype, {
+    k_toeplitz_pad<scalar_t><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(N, C, L, (const scalar_t*)X,
+                                                                            (scalar_t*)xt);
+    return check_launch("k_toeplitz_pad");
+  });
+}
+
+extern "C" int lob_toeplitz_embed(int32_t dtype, int64_t B, int64_t N, int64_t L, const void* col,
+                                  int64_t col_batch_stride, void* c, void* stream) {
+  LOB_REQUIRE(B > 0 && N > 0 && L >= 2 * N - 1, "lob_toeplitz_embed: need L >= 2N-1");
+  LOB_REQUIRE(col && c, "lob_toeplitz_embed: NULL pointer");
+  const int64_t total = B * L;
+  LOB_DISPATCH_DTYPE(dtype, {
+    k_toeplitz_embed<scalar_t><<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        N, L, (const scalar_t*)col, col_batch_stride, (scalar_t*)c, total);
+    return check_launch("k_toeplitz_embed");
+  });
+}
+
+extern "C" int lob_toeplitz_mul(int32_t dtype, int64_t B, int64_t C, int64_t H, const void* fc, int64_t fc_batch_stride,
+                                void* fx, void* stream) {
+  LOB_REQUIRE(B > 0 && C > 0 && H > 0, "lob_toeplitz_mul: sizes must be positive");
+  LOB_REQUIRE(fc && fx, "lob_toeplitz_mul: NULL pointer");
+  const int64_t total = B * C * H;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LOB_F32) {
+    k_toeplitz_mul<float2><<<(unsigned)cdiv(total, 256), 256, 0, st>>>(C, H, (const float2*)fc, fc_batch_stride,
+                                                                      (float2*)fx, total);
+  } else if (dtype == LOB_F64) {
+    k_toeplitz_mul<double2><<<(unsigned)cdiv(total, 256), 256, 0, st>>>(C, H, (const double2*)fc, fc_batch_stride,
+                                                                       (double2*)fx, total);
+  } else {
+    return fail(LOB_ERR_ARG, "dtype must be LOB_F32 or LOB_F64");
+  }
+  return check_launch("k_toeplitz_mul");
+}
+
+extern "C" int lob_toeplitz_unpad(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* yt,
+                                  double scale, const void* X, const void* d, int64_t d_batch_stride, int64_t d_stride,
+                                  void* Y, void* stream) {
+  LOB_REQUIRE(B > 0 && N > 0 && C > 0 && L >= N, "lob_toeplitz_unpad: bad sizes");
+  LOB_REQUIRE(B <= 65535, "lob_toeplitz_unpad: flattened batch > 65535 not supported");
+  LOB_REQUIRE(yt && Y && (!d || X), "lob_toeplitz_unpad: NULL pointer");
+  dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(C, 32), (unsigned)B);
+  LOB_DISPATCH_DTYPE(dtype, {
+    k_toeplitz_unpad<scalar_t><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        N, C, L, (const scalar_t*)yt, (scalar_t)scale, (const scalar_t*)X, (const scalar_t*)d, d_batch_stride,
+        d_stride, (scalar_t*)Y);
+    return check_launch("k_toeplitz_unpad");
+  });
+}
+
+extern "C" size_t lob_cap_solve_workspace_bytes(int64_t B, int32_t k, int64_t C) {
+  if (B <= 0 || k <= 0 || C <= 0) return 0;
+  return (size_t)B * ((size_t)k * k + (size_t)k * C) * sizeof(double);
+}
+
+extern "C" int lob_cap_solve(int32_t dtype, int64_t B, int32_t k, int64_t C, const double* G, int64_t g_batch_stride,
+                             void* W, void* logdet_cap, int32_t* info, void* ws, void* stream) {
+  LOB_REQUIRE(B > 0 && k > 0 && C > 0, "lob_cap_solve: sizes must be positive");
+  LOB_REQUIRE(G && W && logdet_cap && info && ws, "lob_cap_solve: NULL pointer");
+  LOB_DISPATCH_DTYPE(dtype, {
+    k_cap_solve<scalar_t><<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(k, C, G, g_batch_stride, (scalar_t*)W,
+                                                                        (scalar_t*)logdet_cap, info, (double*)ws);
+    return check_launch("k_cap_solve");
+  });
+}

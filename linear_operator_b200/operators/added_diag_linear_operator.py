@@ -1,0 +1,112 @@
+"""AddedDiagLinearOperator: ``A + D`` with the pivoted-Cholesky preconditioner
+(reference: operators/added_diag_linear_operator.py)."""
+from __future__ import annotations
+
+import warnings
+from typing import Callable, Optional, Tuple
+
+import torch
+
+from .. import _kernels, settings
+from ..utils.warnings import NumericalWarning
+from ._linear_operator import LinearOperator
+from .dense_linear_operator import DenseLinearOperator
+from .diag_linear_operator import ConstantDiagLinearOperator, DiagLinearOperator
+from .root_linear_operator import RootLinearOperator
+from .sum_linear_operator import PsdSumLinearOperator, SumLinearOperator
+
+
+class AddedDiagLinearOperator(SumLinearOperator):
+    """``linear_op + diag``; exactly one of the two operands must be a DiagLinearOperator (reference :36-70)."""
+
+    def __init__(self, *linear_ops, preconditioner_override: Optional[Callable] = None):
+        linear_ops = list(linear_ops)
+        super().__init__(*linear_ops, preconditioner_override=preconditioner_override)
+        if len(linear_ops) > 2:
+            raise RuntimeError("An AddedDiagLinearOperator can only have two components")
+        a, b = self.linear_ops
+        if isinstance(a, DiagLinearOperator) and isinstance(b, DiagLinearOperator):
+            raise RuntimeError("Trying to lazily add two DiagLinearOperators. Create a single DiagLinearOperator instead.")
+        elif isinstance(a, DiagLinearOperator):
+            self._diag_tensor, self._linear_op = a, b
+        elif isinstance(b, DiagLinearOperator):
+            self._diag_tensor, self._linear_op = b, a
+        else:
+            raise RuntimeError("One of the LinearOperators input to AddedDiagLinearOperator must be a DiagLinearOperator!")
+        self.preconditioner_override = preconditioner_override
+        self._constant_diag = None
+        self._noise = None
+        self._piv_chol_self = None
+        self._precond_lt = None
+        self._precond_logdet_cache = None
+        self._q_cache = None  # an _kernels.AddedDiagPreconditioner once built (holds Q and logdet M)
+
+    # ------------------------------------------------------------------ matmul: A X + d (.) X in one pass
+    def _matmul(self, rhs):  # :72-76
+        if isinstance(self._linear_op, DenseLinearOperator):
+            return _kernels.dense_matmul(self._linear_op.tensor, rhs, d=self._diag_tensor._diag)
+        fused = getattr(self._linear_op, "_matmul_add_diag", None)
+        if fused is not None:
+            return fused(rhs, self._diag_tensor._diag)
+        out = self._linear_op._matmul(rhs)
+        return out.add_(self._diag_tensor._matmul(rhs))
+
+    def _matmul_closure(self):
+        if isinstance(self._linear_op, DenseLinearOperator):
+            tsr, d = self._linear_op.tensor, self._diag_tensor._diag
+
+            def closure(v):
+                return _kernels.dense_matmul(tsr, v, d=d)
+
+            closure.fused = lambda v: _kernels.dense_matmul(tsr, v, d=d, want_dots=True)
+            return closure
+        return self._matmul
+
+    def add_diagonal(self, diag):  # :78-82
+        return self.__class__(self._linear_op, self._diag_tensor.add_diagonal(diag))
+
+    def __add__(self, other):  # :84-93
+        if isinstance(other, DiagLinearOperator):
+            return self.__class__(self._linear_op, self._diag_tensor + other)
+        return self.__class__(self._linear_op + other, self._diag_tensor)
+
+    # ------------------------------------------------------------------ preconditioner
+    def _preconditioner(self) -> Tuple[Optional[Callable], Optional[LinearOperator], Optional[torch.Tensor]]:
+        """Partial pivoted-Cholesky preconditioner M = L L^T + D (reference :95-142): returns
+        (closure v -> M^-1 v, PsdSum(Root(L), D), logdet M); (None, None, None) when disabled or too small."""
+        if self.preconditioner_override is not None:
+            return self.preconditioner_override(self)
+        if settings.max_preconditioner_size.value() == 0 or self.size(-1) < settings.min_preconditioning_size.value():
+            return None, None, None
+        if self._q_cache is None:
+            max_iter = settings.max_preconditioner_size.value()
+            self._piv_chol_self = self._linear_op.pivoted_cholesky(rank=max_iter)
+            if torch.any(torch.isnan(self._piv_chol_self)).item():  # :126-131
+                warnings.warn(
+                    "NaNs encountered in preconditioner computation. Attempting to continue without preconditioning.",
+                    NumericalWarning,
+                )
+                return None, None, None
+            self._init_cache()
+        return self._q_cache, self._precond_lt, self._precond_logdet_cache
+
+    def _init_cache(self):  # :144-184
+        diag = self._diag_tensor._diagonal()
+        if isinstance(self._diag_tensor, ConstantDiagLinearOperator):
+            self._constant_diag = True
+        else:
+            # the reference decides "constant" at run time by comparing with the first element (:149-150)
+            self._constant_diag = bool(torch.equal(diag, diag[..., :1].expand_as(diag)))
+        self._noise = diag[..., :1] if self._constant_diag else diag
+        self._q_cache = _kernels.AddedDiagPreconditioner(self._piv_chol_self, diag, self._constant_diag)
+        self._precond_logdet_cache = self._q_cache.logdet
+        self._precond_lt = PsdSumLinearOperator(RootLinearOperator(self._piv_chol_self), self._diag_tensor)  # :159
+
+    def _diagonal(self):
+        return self._linear_op._diagonal() + self._diag_tensor._diagonal()
+
+    def _pivoted_cholesky(self, rank, error_tol):
+        raise NotImplementedError
+
+
+__all__ = ["AddedDiagLinearOperator"]

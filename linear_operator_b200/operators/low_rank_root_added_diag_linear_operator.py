@@ -1,0 +1,126 @@
+"""LowRankRootAddedDiagLinearOperator: ``U U^T + D`` solved directly with Woodbury -- CG never runs
+(reference: operators/low_rank_root_added_diag_linear_operator.py:36-193)."""
+from __future__ import annotations
+
+import torch
+
+from .. import _kernels
+from ..utils.memoize import cached
+from .added_diag_linear_operator import AddedDiagLinearOperator
+from .diag_linear_operator import DiagLinearOperator
+from .root_linear_operator import LowRankRootLinearOperator
+
+
+class LowRankRootAddedDiagLinearOperator(AddedDiagLinearOperator):
+    def __init__(self, *linear_ops, preconditioner_override=None):
+        if len(linear_ops) > 2:
+            raise RuntimeError("An AddedDiagLinearOperator can only have two components")
+        if isinstance(linear_ops[0], DiagLinearOperator) and not isinstance(linear_ops[1], LowRankRootLinearOperator):
+            raise RuntimeError(
+                "A LowRankRootAddedDiagLinearOperator can only be created with a LowRankLinearOperator base!"
+            )
+        elif isinstance(linear_ops[1], DiagLinearOperator) and not isinstance(linear_ops[0], LowRankRootLinearOperator):
+            raise RuntimeError(
+                "A LowRankRootAddedDiagLinearOperator can only be created with a LowRankLinearOperator base!"
+            )
+        super().__init__(*linear_ops, preconditioner_override=preconditioner_override)
+
+    def _gram(self):
+        """G = U^T D^-1 U in double, shared by ``_solve`` and ``_logdet`` (the reference caches chol(I + G), :36-47)."""
+        if getattr(self, "_gram_cache", None) is None:
+            U = self._linear_op._root_tensor()
+            d = self._diag_tensor._diag
+            Us = _kernels.scale_rows(U, d, "div_sqrt")  # D^-1/2 U
+            self._gram_cache = _kernels.tn_matmul(Us, Us, out_dtype=torch.float64)
+        return self._gram_cache
+
+    def _preconditioner(self):
+        return None, None, None
+
+    def _solve_preconditioner(self):
+        return None
+
+    def _solve(self, rhs, preconditioner=None, num_tridiag=0):  # :62-87
+        U = self._linear_op._root_tensor()
+        d = self._diag_tensor._diag
+        dinv_b = _kernels.scale_rows(rhs, d, "div")  # D^-1 b
+        w = _kernels.tn_matmul(U, dinv_b)  # U^T D^-1 b
+        w, _, _ = _kernels.cap_solve(self._gram(), w)  # (I + U^T D^-1 U)^-1 .
+        res = _kernels.scale_rows(_kernels.matmul_nn(U, w), d, "div")  # D^-1 U .
+        return dinv_b.sub_(res)
+
+    def _logdet(self):  # :95-101
+        U = self._linear_op._root_tensor()
+        k = U.shape[-1]
+        dummy = torch.zeros(*self.batch_shape, k, 1, dtype=self.dtype, device=self.device)
+        _, logdet_cap, _ = _kernels.cap_solve(self._gram(), dummy)
+        return logdet_cap + self._diag_tensor.logdet()
+
+    def inv_quad_logdet(self, inv_quad_rhs=None, logdet=False, reduce_inv_quad=True):  # :114-160
+        if not self.is_square:
+            raise RuntimeError(
+                "inv_quad_logdet only operates on (batches of) square (positive semi-definite) LinearOperators. "
+                "Got a {} of size {}.".format(self.__class__.__name__, self.size())
+            )
+        if inv_quad_rhs is not None:
+            if self.dim() == 2 and inv_quad_rhs.dim() == 1:
+                if self.shape[-1] != inv_quad_rhs.numel():
+                    raise RuntimeError(
+                        "LinearOperator (size={}) cannot be multiplied with right-hand-side Tensor (size={}).".format(
+                            self.shape, inv_quad_rhs.shape
+                        )
+                    )
+            elif self.dim() != inv_quad_rhs.dim():
+                raise RuntimeError(
+                    "LinearOperator (size={}) and right-hand-side Tensor (size={}) should have the same number "
+                    "of dimensions.".format(self.shape, inv_quad_rhs.shape)
+                )
+            elif self.batch_shape != inv_quad_rhs.shape[:-2] or self.shape[-1] != inv_quad_rhs.shape[-2]:
+                raise RuntimeError(
+                    "LinearOperator (size={}) cannot be multiplied with right-hand-side Tensor (size={}).".format(
+                        self.shape, inv_quad_rhs.shape
+                    )
+                )
+        inv_quad_term, logdet_term = None, None
+        if inv_quad_rhs is not None:
+            rhs = inv_quad_rhs.unsqueeze(-1) if inv_quad_rhs.dim() == 1 else inv_quad_rhs
+            sol = self._solve(rhs)
+            inv_quad_term = _kernels.col_dots(rhs, 0, sol, 0, rhs.shape[-1])
+            if inv_quad_rhs.dim() == 1:
+                inv_quad_term = inv_quad_term.squeeze(-1)
+            elif reduce_inv_quad:
+                inv_quad_term = inv_quad_term.sum(dim=-1)
+        if logdet:
+            logdet_term = self._logdet()
+        return inv_quad_term, logdet_term
+
+    def solve(self, right_tensor, left_tensor=None):  # :162-193
+        if not self.is_square:
+            raise RuntimeError(
+                "solve only operates on (batches of) square (positive semi-definite) LinearOperators. "
+                "Got a {} of size {}.".format(self.__class__.__name__, self.size())
+            )
+        if self.dim() == 2 and right_tensor.dim() == 1:
+            if self.shape[-1] != right_tensor.numel():
+                raise RuntimeError(
+                    "LinearOperator (size={}) cannot be multiplied with right-hand-side Tensor (size={}).".format(
+                        self.shape, right_tensor.shape
+                    )
+                )
+        squeeze = right_tensor.ndimension() == 1
+        rhs = right_tensor.unsqueeze(-1) if squeeze else right_tensor
+        sol = self._solve(rhs)
+        if squeeze:
+            sol = sol.squeeze(-1)
+        return sol if left_tensor is None else left_tensor @ sol
+
+    def logdet(self):
+        return self._logdet()
+
+    def __add__(self, other):
+        if isinstance(other, DiagLinearOperator):
+            return self.__class__(self._linear_op, self._diag_tensor + other)
+        return AddedDiagLinearOperator(self._linear_op + other, self._diag_tensor)
+
+
+__all__ = ["LowRankRootAddedDiagLinearOperator"]
