@@ -120,7 +120,7 @@ def test_cg_nonconvergence_warns():
     a = a @ a.mT + 1e-3 * torch.eye(60, dtype=torch.float64, device=DEV)
     b = torch.randn(60, 2, dtype=torch.float64, device=DEV)
     with pytest.warns(lo.utils.warnings.NumericalWarning):
-        linear_cg(a, b, max_iter=12, tolerance=1e-12)
+        linear_cg(a, b, max_iter=25, tolerance=1e-12)
 
 
 # ------------------------------------------------------------------------------------------------------------
