@@ -15,6 +15,11 @@ from . import _lib
 from ._lib import check, dt, ptr, require_cuda, stream, workspace
 
 
+# bench.py sets this to a list to collect (start, end) CUDA events around every dense operator matmul launch, recorded
+# on the launching stream (roofline.achieved is derived from them).  None = no profiling.
+PROFILE_MATMUL = None
+
+
 def _flat3(t: torch.Tensor) -> torch.Tensor:
     """(*batch, R, C) -> contiguous (B, R, C)"""
     t = t.contiguous()
@@ -69,11 +74,18 @@ def dense_matmul(A: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = N
     n_parts = int(lib.lob_dense_matmul_parts(M))
     if want_dots:
         dots = torch.empty(B, n_parts, C, dtype=torch.float64, device=X.device)
+    prof = PROFILE_MATMUL
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(
         lib.lob_dense_matmul(dt(X), B, M, K, C, ptr(Af), lda, a_bs, ptr(Xf), ptr(Y), ptr(dd), d_bs, d_st, ptr(dots),
                              stream(X)),
         "lob_dense_matmul",
     )
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1))
     Y = Y.reshape(*batch_shape, M, C)
     if want_dots:
         return Y, dots, n_parts
