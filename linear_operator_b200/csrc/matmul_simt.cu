@@ -9,6 +9,8 @@
 // Both use a 128 x (8*RN) output tile per CTA, 256 threads as 32 (row groups of 4) x 8 (column groups of RN),
 // operands staged through shared memory in k-major order so the inner product reads one 128-bit word of A and RN
 // words of B per 4*RN FMAs.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "simt_tile.cuh"
 
@@ -266,6 +268,12 @@ extern "C" int lob_matmul_nn(int32_t dtype, int64_t B, int64_t M, int64_t K, int
   });
 }
 
+namespace lob {
+int dense_matmul_tc_f32(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
+                        const float* X, float* Y, const float* d, int64_t d_bs, int64_t d_st, double* dots,
+                        cudaStream_t st);
+}
+
 extern "C" int lob_dense_matmul(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A, int64_t lda,
                                 int64_t a_batch_stride, const void* X, void* Y, const void* d, int64_t d_batch_stride,
                                 int64_t d_stride, double* dots, void* stream) {
@@ -273,6 +281,12 @@ extern "C" int lob_dense_matmul(int32_t dtype, int64_t B, int64_t M, int64_t K, 
   LOB_REQUIRE(B <= 65535, "lob_dense_matmul: flattened batch > 65535 not supported");
   LOB_REQUIRE(A && X && Y, "lob_dense_matmul: NULL pointer");
   LOB_REQUIRE((!d && !dots) || M == K, "lob_dense_matmul: fused diagonal / dots need a square operator");
+  if (dtype == LOB_F32 && !getenv("LOB_DISABLE_TC")) {
+    // tensor-core path (dense_tc.cu); shapes it does not cover fall through to the CUDA-core kernel
+    int s = dense_matmul_tc_f32(B, M, K, C, (const float*)A, lda, a_batch_stride, (const float*)X, (float*)Y,
+                                (const float*)d, d_batch_stride, d_stride, dots, (cudaStream_t)stream);
+    if (s != LOB_ERR_UNSUPPORTED) return s;
+  }
   LOB_DISPATCH_DTYPE(dtype, {
     return launch_nn<scalar_t>(B, M, K, C, (const scalar_t*)A, lda, a_batch_stride, (const scalar_t*)X, K * C,
                                (scalar_t*)Y, (const scalar_t*)d, d_batch_stride, d_stride, dots, 0.0,

@@ -1,0 +1,64 @@
+"""The tcgen05 3xTF32 dense operator matmul (csrc/dense_tc.cu) against an fp64 product of the same fp32 inputs and
+against the CUDA-core kernel.  fp32 inputs; the bar is fp32 accuracy (error << 1e-4, north-star parity tolerance)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from linear_operator_b200 import _kernels  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _case(B, N, C, with_diag, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    A = torch.randn(B, N, N, device=DEV, generator=g) / N**0.5
+    X = torch.randn(B, N, C, device=DEV, generator=g)
+    d = (0.1 + torch.rand(B, N, device=DEV, generator=g)) if with_diag else None
+    ref = A.double() @ X.double()
+    if with_diag:
+        ref = ref + d.double().unsqueeze(-1) * X.double()
+    return A, X, d, ref
+
+
+@pytest.mark.parametrize(
+    "B,N,C,with_diag",
+    [(2, 384, 33, True), (1, 260, 1, False), (2, 1000, 17, True), (2, 512, 48, True), (3, 2052, 33, True),
+     (1, 128, 8, False), (2, 5000, 33, True)],
+)
+def test_dense_tc_matches_fp64(B, N, C, with_diag):
+    A, X, d, ref = _case(B, N, C, with_diag, 100 + N + C)
+    Y, dots, n_parts = _kernels.dense_matmul(A, X, d=d, want_dots=True)
+    torch.cuda.synchronize()
+    scale = ref.abs().max()
+    err = ((Y.double() - ref).abs().max() / scale).item()
+    assert err < 3e-6, f"tensor-core matmul error {err}"
+    dots_ref = (X.double() * ref).sum(-2)
+    derr = ((dots.sum(1) - dots_ref).abs().max() / dots_ref.abs().max()).item()
+    assert derr < 3e-6, f"fused <x,y> partials error {derr}"
+    # same call through the CUDA-core kernel
+    os.environ["LOB_DISABLE_TC"] = "1"
+    try:
+        Y2 = _kernels.dense_matmul(A, X, d=d)
+    finally:
+        del os.environ["LOB_DISABLE_TC"]
+    err2 = ((Y2.double() - ref).abs().max() / scale).item()
+    assert err2 < 3e-6
+    assert ((Y - Y2).abs().max() / scale).item() < 3e-6
+
+
+def test_dense_tc_plain_tf32_would_fail():
+    """Sanity of the bar itself: a single-pass TF32 product is ~1e-3 off, the 3xTF32 kernel is not."""
+    A, X, d, ref = _case(1, 1024, 33, False, 7)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        tf32 = A @ X
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    e_tf32 = ((tf32.double() - ref).abs().max() / ref.abs().max()).item()
+    Y = _kernels.dense_matmul(A, X)
+    e_ours = ((Y.double() - ref).abs().max() / ref.abs().max()).item()
+    assert e_ours < 3e-6 and e_ours < e_tf32 / 20
