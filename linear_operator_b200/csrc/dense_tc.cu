@@ -69,6 +69,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// tf32 with round-to-nearest (ties away from zero) as two integer ops: add half an ulp of the 10-bit mantissa to the
+// sign-magnitude bit pattern, clear the 13 low bits (same result as cvt.rna.tf32.f32, which issues at conversion rate).
+// hi = rna(a), lo = rna(a - hi): an unbiased split; a - hi is exact in fp32.
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -242,33 +247,57 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
     }
   } else if (warp < 4) {
     // ===================== X producers: split + transpose into [X_hi ; X_lo] =====================
+    // The 32 x C block of X is one contiguous run of 32*C floats.  Thread i of the 64 owns elements i, i+64, ...;
+    // their (k, c) coordinates -- hence the swizzled destination offsets -- do not depend on the k-block, so they are
+    // computed once.  Loads of block kb+1 are issued before block kb is written (register prefetch) so the global /
+    // L2 latency hides behind one k-block of work.
+    constexpr int NE = (TC_BK * CP + 63) / 64;
     const int tid2 = threadIdx.x - 64;  // 0..63
     const float* Xb = p.X + b * p.K * p.C;
     const int C = (int)p.C;
+    const int total = TC_BK * C;
+    uint32_t off[NE];
+    int kk[NE];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const int e = tid2 + i * 64;
+      const int k = e / C, c = e - k * C;
+      kk[i] = (e < total) ? k : TC_BK;  // TC_BK = never valid
+      off[i] = (uint32_t)c * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)c & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
+    }
+    float cur[NE], nxt[NE];
+    {
+      const int kvalid = (int)min((int64_t)TC_BK, p.K);
+#pragma unroll
+      for (int i = 0; i < NE; ++i) cur[i] = (kk[i] < kvalid) ? __ldg(Xb + tid2 + i * 64) : 0.f;
+    }
     for (int kb = 0; kb < nkb; ++kb) {
       const int sb = kb % TC_NSB;
       const uint32_t phb = (kb / TC_NSB) & 1;
+      if (kb + 1 < nkb) {
+        const int64_t k1 = (int64_t)(kb + 1) * TC_BK;
+        const int kvalid = (int)min((int64_t)TC_BK, p.K - k1);
+        const float* src = Xb + k1 * C + tid2;
+#pragma unroll
+        for (int i = 0; i < NE; ++i) nxt[i] = (kk[i] < kvalid) ? __ldg(src + i * 64) : 0.f;
+      }
       mbar_wait(smem_u32(&empty_b[sb]), phb ^ 1);
       unsigned char* dst = sB + sb * B_STAGE;
-      const int64_t k0 = (int64_t)kb * TC_BK;
-      const int kvalid = (int)min((int64_t)TC_BK, p.K - k0);
-      const int total = TC_BK * C;
-      const float* src = Xb + k0 * C;
-      for (int e = tid2; e < total; e += 64) {
-        const int k = e / C, c = e - k * C;
-        float v = 0.f;
-        if (k < kvalid) v = __ldg(src + e);
-        const uint32_t hi_bits = __float_as_uint(v) & 0xFFFFE000u;
-        const float hi = __uint_as_float(hi_bits);
-        const float lo = v - hi;
-        const uint32_t off = (uint32_t)c * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)c & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
-        *reinterpret_cast<float*>(dst + off) = hi;
-        // rows CP.. hold X_lo; CP is a multiple of 8 so the swizzle phase (row & 7) is unchanged
-        *reinterpret_cast<uint32_t*>(dst + off + CP * 128) = __float_as_uint(lo) & 0xFFFFE000u;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        if (kk[i] < TC_BK) {
+          const uint32_t hi_bits = tf32_rna(cur[i]);
+          const float lo = cur[i] - __uint_as_float(hi_bits);
+          *reinterpret_cast<uint32_t*>(dst + off[i]) = hi_bits;
+          // rows CP.. hold X_lo; CP is a multiple of 8 so the swizzle phase (row & 7) is unchanged
+          *reinterpret_cast<uint32_t*>(dst + off[i] + CP * 128) = tf32_rna(lo);
+        }
       }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&full_b[sb]));
+#pragma unroll
+      for (int i = 0; i < NE; ++i) cur[i] = nxt[i];
     }
   } else {
     // ===================== converters (then epilogue) =====================
@@ -291,9 +320,9 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint32_t h = w[q] & 0xFFFFE000u;
+          const uint32_t h = tf32_rna(__uint_as_float(w[q]));
           hi[j * 4 + q] = h;
-          lo[j * 4 + q] = __float_as_uint(__uint_as_float(w[q]) - __uint_as_float(h));
+          lo[j * 4 + q] = tf32_rna(__uint_as_float(w[q]) - __uint_as_float(h));
         }
       }
       __syncwarp();
