@@ -154,7 +154,8 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
   constexpr uint32_t IDESC_NARROW = make_idesc_tf32(128, CP);
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // pad to a 1024-byte boundary with pointer arithmetic on the __shared__ array (keeps LDS/STS code generation)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;                                  // TC_NSA * 32 KB
   unsigned char* sB = smem + TC_NSA * TC_A_STAGE;            // TC_NSB * B_STAGE
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + TC_NSB * B_STAGE);
@@ -217,33 +218,44 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int t = kb & 1;
-      const uint32_t pht = (kb >> 1) & 1;
-      const int sb = kb % TC_NSB;
-      const uint32_t phb = (kb / TC_NSB) & 1;
-      mbar_wait(smem_u32(&tm_full[t]), pht);
-      mbar_wait(smem_u32(&full_b[sb]), phb);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB + sb * B_STAGE));
+    // Unrolled by 6 = lcm(2 TMEM slots, 3 X stages): every TMEM address and smem descriptor below is then a
+    // loop-invariant base plus a compile-time offset, which keeps the per-MMA issue sequence short.
+    static_assert(TC_NSB == 3, "the MMA issue loop is unrolled for 3 X stages");
+    const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(sB));
+    for (int kb0 = 0; kb0 < nkb; kb0 += 6) {
 #pragma unroll
-        for (int tile = 0; tile < 2; ++tile) {
-          const uint32_t d_addr = tmem_base + tile * D_STRIDE;
-          const uint32_t a_hi = tmem_base + SLOT0 + t * SLOT_COLS + tile * 64;
-          const uint32_t a_lo = a_hi + 32;
+      for (int u = 0; u < 6; ++u) {
+        const int kb = kb0 + u;
+        if (kb >= nkb) break;
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int t = u & 1;
+        const int sb = u % 3;
+        const uint32_t pht = (kb >> 1) & 1;
+        const uint32_t phb = (kb / TC_NSB) & 1;
+        mbar_wait(smem_u32(&tm_full[t]), pht);
+        mbar_wait(smem_u32(&full_b[sb]), phb);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t bdesc = bdesc0 + (uint64_t)((sb * B_STAGE) >> 4);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t bd = bdesc + (uint64_t)((k * 32) >> 4);  // advance 8 tf32 = 32 bytes inside the swizzle span
-            umma_tf32_ts(d_addr, a_hi + k * 8, bd, IDESC_WIDE, (kb | k) ? 1u : 0u);
-            umma_tf32_ts(d_addr, a_lo + k * 8, bd, IDESC_NARROW, 1u);
+          for (int tile = 0; tile < 2; ++tile) {
+            const uint32_t d_addr = tmem_base + tile * D_STRIDE;
+            const uint32_t a_hi = tmem_base + SLOT0 + t * SLOT_COLS + tile * 64;
+            const uint32_t a_lo = a_hi + 32;
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k) {
+              const uint64_t bd = bdesc + (uint64_t)((k * 32) >> 4);  // 8 tf32 = 32 bytes inside the swizzle span
+              umma_tf32_ts(d_addr, a_hi + k * 8, bd, IDESC_WIDE, (kb | k) ? 1u : 0u);
+              umma_tf32_ts(d_addr, a_lo + k * 8, bd, IDESC_NARROW, 1u);
+            }
           }
+          umma_commit(smem_u32(&tm_empty[t]));
+          umma_commit(smem_u32(&empty_b[sb]));
+          if (kb == nkb - 1) umma_commit(smem_u32(acc_full));
         }
-        umma_commit(smem_u32(&tm_empty[t]));
-        umma_commit(smem_u32(&empty_b[sb]));
-        if (kb == nkb - 1) umma_commit(smem_u32(acc_full));
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp < 4) {
     // ===================== X producers: split + transpose into [X_hi ; X_lo] =====================
@@ -265,29 +277,26 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
       kk[i] = (e < total) ? k : TC_BK;  // TC_BK = never valid
       off[i] = (uint32_t)c * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)c & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
     }
-    float cur[NE], nxt[NE];
-    {
-      const int kvalid = (int)min((int64_t)TC_BK, p.K);
-#pragma unroll
-      for (int i = 0; i < NE; ++i) cur[i] = (kk[i] < kvalid) ? __ldg(Xb + tid2 + i * 64) : 0.f;
-    }
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int sb = kb % TC_NSB;
-      const uint32_t phb = (kb / TC_NSB) & 1;
-      if (kb + 1 < nkb) {
-        const int64_t k1 = (int64_t)(kb + 1) * TC_BK;
+    float r0[NE], r1[NE];
+    auto load_block = [&](float (&reg)[NE], int kb) {
+      if (kb < nkb) {
+        const int64_t k1 = (int64_t)kb * TC_BK;
         const int kvalid = (int)min((int64_t)TC_BK, p.K - k1);
         const float* src = Xb + k1 * C + tid2;
 #pragma unroll
-        for (int i = 0; i < NE; ++i) nxt[i] = (kk[i] < kvalid) ? __ldg(src + i * 64) : 0.f;
+        for (int i = 0; i < NE; ++i) reg[i] = (kk[i] < kvalid) ? __ldg(src + i * 64) : 0.f;
       }
+    };
+    auto store_block = [&](const float (&reg)[NE], int kb) {
+      const int sb = kb % TC_NSB;
+      const uint32_t phb = (kb / TC_NSB) & 1;
       mbar_wait(smem_u32(&empty_b[sb]), phb ^ 1);
       unsigned char* dst = sB + sb * B_STAGE;
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
         if (kk[i] < TC_BK) {
-          const uint32_t hi_bits = tf32_rna(cur[i]);
-          const float lo = cur[i] - __uint_as_float(hi_bits);
+          const uint32_t hi_bits = tf32_rna(reg[i]);
+          const float lo = reg[i] - __uint_as_float(hi_bits);
           *reinterpret_cast<uint32_t*>(dst + off[i]) = hi_bits;
           // rows CP.. hold X_lo; CP is a multiple of 8 so the swizzle phase (row & 7) is unchanged
           *reinterpret_cast<uint32_t*>(dst + off[i] + CP * 128) = tf32_rna(lo);
@@ -296,8 +305,16 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&full_b[sb]));
-#pragma unroll
-      for (int i = 0; i < NE; ++i) cur[i] = nxt[i];
+    };
+    load_block(r0, 0);
+    load_block(r1, 1);
+    for (int kb = 0; kb < nkb; kb += 2) {
+      store_block(r0, kb);
+      load_block(r0, kb + 2);
+      if (kb + 1 < nkb) {
+        store_block(r1, kb + 1);
+        load_block(r1, kb + 3);
+      }
     }
   } else {
     // ===================== converters (then epilogue) =====================
