@@ -11,11 +11,13 @@
 // 32-column blocks of A.  Warp roles (12 warps):
 //   warp 0      : TMA producer -- one 256 x 32 fp32 box of A per k-block (32 KB, 128B-swizzled) into a 5-stage ring
 //   warp 1      : MMA issuer   -- one elected lane issues tcgen05.mma.kind::tf32 (A from TMEM, B from smem)
-//   warps 2-3   : X producers  -- load the 32 x C block of X, split it into tf32 hi / lo, write it transposed
-//                                 (K-major, 128B swizzle) into a 3-stage ring as the stacked operand [X_hi ; X_lo]
+//   warps 2-3   : idle (reserved)
 //   warps 4-11  : converters   -- read their row of the A tile from smem, split into hi = tf32(a), lo = a - hi, and
-//                                 tcgen05.st both halves into a double-buffered TMEM operand slot; afterwards the
-//                                 same warps run the epilogue (tcgen05.ld, + d x, <x,y> partials, coalesced store)
+//                                 tcgen05.st both halves into a double-buffered TMEM operand slot; the same 256
+//                                 threads also produce the X operand: each loads a few elements of the 32 x C block
+//                                 of X (register-prefetched two k-blocks ahead), splits them and writes them
+//                                 transposed (K-major, 128B swizzle) into a 3-stage ring as [X_hi ; X_lo]; afterwards
+//                                 they run the epilogue (tcgen05.ld, + d x, <x,y> partials, coalesced store)
 // Per k-block and M tile:  D[:, 0:2Cp] += A_hi [X_hi ; X_lo]^T   (one N = 2*Cp MMA per 8-wide k step)
 //                          D[:, 0:Cp]  += A_lo  X_hi^T           (one N = Cp MMA)
 // and y = D[:, c] + D[:, Cp + c]: the three products of the 3xTF32 scheme with fp32 accumulation in TMEM.
@@ -78,18 +80,27 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// Both helpers are executed by ALL lanes of the issuing warp (convergent, warp-uniform operands); the PTX predicate
+// `leader` restricts the instruction to one lane.  Branching on the lane in C++ instead makes the compiler wrap every
+// tcgen05 instruction in an elect/loop sequence (~80 issue cycles per MMA, measured).
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar), "r"(leader)
+      : "memory");
 }
 
 // D[tmem] (+)= A[tmem] * B[smem desc]
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate) {
+                                             uint32_t accumulate, uint32_t leader) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
 
@@ -161,9 +172,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + TC_NSB * B_STAGE);
   uint64_t* full_a = bars;                   // [NSA]  TMA -> converters
   uint64_t* empty_a = full_a + TC_NSA;       // [NSA]  converters -> TMA
-  uint64_t* full_b = empty_a + TC_NSA;       // [NSB]  X producers -> MMA
-  uint64_t* empty_b = full_b + TC_NSB;       // [NSB]  MMA -> X producers
-  uint64_t* tm_full = empty_b + TC_NSB;      // [2]    converters -> MMA
+  uint64_t* tm_full = empty_a + TC_NSA;      // [2]    converters -> MMA (TMEM A slot AND the X stage of that k-block)
   uint64_t* tm_empty = tm_full + 2;          // [2]    MMA -> converters
   uint64_t* acc_full = tm_empty + 2;         // [1]    MMA -> epilogue
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -179,10 +188,6 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
     for (int i = 0; i < TC_NSA; ++i) {
       mbar_init(smem_u32(&full_a[i]), 1);
       mbar_init(smem_u32(&empty_a[i]), 8);
-    }
-    for (int i = 0; i < TC_NSB; ++i) {
-      mbar_init(smem_u32(&full_b[i]), 2);
-      mbar_init(smem_u32(&empty_b[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tm_full[i]), 8);
@@ -219,103 +224,39 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // Unrolled by 6 = lcm(2 TMEM slots, 3 X stages): every TMEM address and smem descriptor below is then a
-    // loop-invariant base plus a compile-time offset, which keeps the per-MMA issue sequence short.
+    // loop-invariant base plus a compile-time offset.  All 32 lanes run this code; lane 0 is the issuing lane.
     static_assert(TC_NSB == 3, "the MMA issue loop is unrolled for 3 X stages");
     const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(sB));
+    const uint32_t leader = (lane == 0) ? 1u : 0u;
     for (int kb0 = 0; kb0 < nkb; kb0 += 6) {
 #pragma unroll
       for (int u = 0; u < 6; ++u) {
         const int kb = kb0 + u;
         if (kb >= nkb) break;
-        constexpr int dummy = 0;
-        (void)dummy;
         const int t = u & 1;
         const int sb = u % 3;
         const uint32_t pht = (kb >> 1) & 1;
-        const uint32_t phb = (kb / TC_NSB) & 1;
         mbar_wait(smem_u32(&tm_full[t]), pht);
-        mbar_wait(smem_u32(&full_b[sb]), phb);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t bdesc = bdesc0 + (uint64_t)((sb * B_STAGE) >> 4);
+        const uint64_t bdesc = bdesc0 + (uint64_t)((sb * B_STAGE) >> 4);
 #pragma unroll
-          for (int tile = 0; tile < 2; ++tile) {
-            const uint32_t d_addr = tmem_base + tile * D_STRIDE;
-            const uint32_t a_hi = tmem_base + SLOT0 + t * SLOT_COLS + tile * 64;
-            const uint32_t a_lo = a_hi + 32;
+        for (int tile = 0; tile < 2; ++tile) {
+          const uint32_t d_addr = tmem_base + tile * D_STRIDE;
+          const uint32_t a_hi = tmem_base + SLOT0 + t * SLOT_COLS + tile * 64;
+          const uint32_t a_lo = a_hi + 32;
 #pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k) {
-              const uint64_t bd = bdesc + (uint64_t)((k * 32) >> 4);  // 8 tf32 = 32 bytes inside the swizzle span
-              umma_tf32_ts(d_addr, a_hi + k * 8, bd, IDESC_WIDE, (kb | k) ? 1u : 0u);
-              umma_tf32_ts(d_addr, a_lo + k * 8, bd, IDESC_NARROW, 1u);
-            }
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t bd = bdesc + (uint64_t)((k * 32) >> 4);  // 8 tf32 = 32 bytes inside the swizzle span
+            umma_tf32_ts(d_addr, a_hi + k * 8, bd, IDESC_WIDE, (kb | k) ? 1u : 0u, leader);
+            umma_tf32_ts(d_addr, a_lo + k * 8, bd, IDESC_NARROW, 1u, leader);
           }
-          umma_commit(smem_u32(&tm_empty[t]));
-          umma_commit(smem_u32(&empty_b[sb]));
-          if (kb == nkb - 1) umma_commit(smem_u32(acc_full));
         }
-        __syncwarp();
+        umma_commit(smem_u32(&tm_empty[t]), leader);
+        if (kb == nkb - 1) umma_commit(smem_u32(acc_full), leader);
       }
     }
   } else if (warp < 4) {
-    // ===================== X producers: split + transpose into [X_hi ; X_lo] =====================
-    // The 32 x C block of X is one contiguous run of 32*C floats.  Thread i of the 64 owns elements i, i+64, ...;
-    // their (k, c) coordinates -- hence the swizzled destination offsets -- do not depend on the k-block, so they are
-    // computed once.  Loads of block kb+1 are issued before block kb is written (register prefetch) so the global /
-    // L2 latency hides behind one k-block of work.
-    constexpr int NE = (TC_BK * CP + 63) / 64;
-    const int tid2 = threadIdx.x - 64;  // 0..63
-    const float* Xb = p.X + b * p.K * p.C;
-    const int C = (int)p.C;
-    const int total = TC_BK * C;
-    uint32_t off[NE];
-    int kk[NE];
-#pragma unroll
-    for (int i = 0; i < NE; ++i) {
-      const int e = tid2 + i * 64;
-      const int k = e / C, c = e - k * C;
-      kk[i] = (e < total) ? k : TC_BK;  // TC_BK = never valid
-      off[i] = (uint32_t)c * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)c & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
-    }
-    float r0[NE], r1[NE];
-    auto load_block = [&](float (&reg)[NE], int kb) {
-      if (kb < nkb) {
-        const int64_t k1 = (int64_t)kb * TC_BK;
-        const int kvalid = (int)min((int64_t)TC_BK, p.K - k1);
-        const float* src = Xb + k1 * C + tid2;
-#pragma unroll
-        for (int i = 0; i < NE; ++i) reg[i] = (kk[i] < kvalid) ? __ldg(src + i * 64) : 0.f;
-      }
-    };
-    auto store_block = [&](const float (&reg)[NE], int kb) {
-      const int sb = kb % TC_NSB;
-      const uint32_t phb = (kb / TC_NSB) & 1;
-      mbar_wait(smem_u32(&empty_b[sb]), phb ^ 1);
-      unsigned char* dst = sB + sb * B_STAGE;
-#pragma unroll
-      for (int i = 0; i < NE; ++i) {
-        if (kk[i] < TC_BK) {
-          const uint32_t hi_bits = tf32_rna(reg[i]);
-          const float lo = reg[i] - __uint_as_float(hi_bits);
-          *reinterpret_cast<uint32_t*>(dst + off[i]) = hi_bits;
-          // rows CP.. hold X_lo; CP is a multiple of 8 so the swizzle phase (row & 7) is unchanged
-          *reinterpret_cast<uint32_t*>(dst + off[i] + CP * 128) = tf32_rna(lo);
-        }
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&full_b[sb]));
-    };
-    load_block(r0, 0);
-    load_block(r1, 1);
-    for (int kb = 0; kb < nkb; kb += 2) {
-      store_block(r0, kb);
-      load_block(r0, kb + 2);
-      if (kb + 1 < nkb) {
-        store_block(r1, kb + 1);
-        load_block(r1, kb + 3);
-      }
-    }
+    // reserved
   } else {
     // ===================== converters (then epilogue) =====================
     const int cw = warp - 4;            // 0..7
@@ -323,7 +264,35 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;  // row inside the M tile == TMEM lane
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    for (int kb = 0; kb < nkb; ++kb) {
+
+    // X operand: the 32 x C block of X is one contiguous run of 32*C floats; converter thread j of 256 owns elements
+    // j, j+256, ...  Their (k, c) coordinates -- hence the swizzled destination offsets -- do not depend on the
+    // k-block, so they are computed once; the values are prefetched two k-blocks ahead into two register sets.
+    constexpr int NE = (TC_BK * CP + 255) / 256;
+    const int ctid = threadIdx.x - 128;  // 0..255
+    const float* Xb = p.X + b * p.K * p.C;
+    const int C = (int)p.C;
+    const int total = TC_BK * C;
+    uint32_t off[NE];
+    int kk[NE];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const int e = ctid + i * 256;
+      const int k = e / C, c = e - k * C;
+      kk[i] = (e < total) ? k : TC_BK;  // TC_BK = never valid
+      off[i] = (uint32_t)c * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)c & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
+    }
+    float x0[NE], x1[NE];
+    auto load_x = [&](float (&reg)[NE], int kb) {
+      if (kb < nkb) {
+        const int64_t k1 = (int64_t)kb * TC_BK;
+        const int kvalid = (int)min((int64_t)TC_BK, p.K - k1);
+        const float* src = Xb + k1 * C + ctid;
+#pragma unroll
+        for (int i = 0; i < NE; ++i) reg[i] = (kk[i] < kvalid) ? __ldg(src + i * 256) : 0.f;
+      }
+    };
+    auto convert_block = [&](const float (&xr)[NE], int kb) {
       const int s = kb % TC_NSA;
       const uint32_t ph = (kb / TC_NSA) & 1;
       const int t = kb & 1;
@@ -344,28 +313,49 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&empty_a[s]));  // smem stage consumed (values are in registers)
+      // MMA(kb-2) retired: TMEM slot t is free, and so is X stage kb % 3 (last read by MMA(kb-3))
       mbar_wait(smem_u32(&tm_empty[t]), pht ^ 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + SLOT0 + t * SLOT_COLS + tile * 64;
       TC_ST32(taddr, hi);
       TC_ST32(taddr + 32, lo);
+      unsigned char* dst = sB + (kb % TC_NSB) * B_STAGE;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        if (kk[i] < TC_BK) {
+          const uint32_t hi_bits = tf32_rna(xr[i]);
+          const float xlo = xr[i] - __uint_as_float(hi_bits);
+          *reinterpret_cast<uint32_t*>(dst + off[i]) = hi_bits;
+          // rows CP.. hold X_lo; CP is a multiple of 8 so the swizzle phase (row & 7) is unchanged
+          *reinterpret_cast<uint32_t*>(dst + off[i] + CP * 128) = tf32_rna(xlo);
+        }
+      }
+      fence_async_smem();
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tm_full[t]));
+    };
+    load_x(x0, 0);
+    load_x(x1, 1);
+    for (int kb = 0; kb < nkb; kb += 2) {
+      convert_block(x0, kb);
+      load_x(x0, kb + 2);
+      if (kb + 1 < nkb) {
+        convert_block(x1, kb + 1);
+        load_x(x1, kb + 3);
+      }
     }
 
     // ---------------- epilogue ----------------
     mbar_wait(smem_u32(acc_full), 0);
     tc_fence_after();
-    const int C = (int)p.C;
     // staging (aliases the A ring, which is fully consumed): per tile xs[128][C], ys[128][C]
     float* xs = reinterpret_cast<float*>(sA) + tile * (2 * 128 * 49);
     float* ys = xs + 128 * 49;
     const int64_t tile_m0 = m0 + tile * 128;
     const int rows_valid = (int)max((int64_t)0, min((int64_t)128, p.M - tile_m0));
     const int ct = threadIdx.x - 128 - tile * 128;  // 0..127 within the tile's 4 warps
-    const float* Xb = p.X + b * p.K * p.C;
     float* Yb = p.Y + b * p.M * p.C;
     const bool need_x = (p.dg != nullptr) || (p.dots != nullptr);
     if (need_x) {
