@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_int32, c_int64, c_s
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblob_b200.so")
+LIB_PATH = os.environ.get("LOB_LIB_PATH", os.path.join(_HERE, "csrc", "liblob_b200.so"))
 
 F32, F64 = 0, 1
 _DT = {torch.float32: F32, torch.float64: F64}

@@ -23,6 +23,7 @@
 // and y = D[:, c] + D[:, Cp + c]: the three products of the 3xTF32 scheme with fp32 accumulation in TMEM.
 // The dropped a_lo * x_lo term is O(2^-22) relative.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -64,6 +65,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Warp-collective wait (all 32 lanes call it): every lane polls, the loop exit is decided by a warp vote, so the warp
+// leaves the loop CONVERGED.  This matters: tcgen05.ld/st/wait are .sync.aligned, and the elect.sync inside the MMA /
+// commit helpers is compiled to a plain ELECT over the currently active lanes -- if lanes left a spin loop one by one,
+// each convergence group would elect its own leader and issue the MMA (or the commit) again.  Observed as percent-level
+// errors and early barrier phases before this helper existed.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (__all_sync(0xffffffffu, ok != 0)) return;
+    if (clock64() - t0 > TC_SPIN_CYCLES) __trap();
+  }
+}
+
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -80,13 +102,16 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Both helpers are executed by ALL lanes of the issuing warp (convergent, warp-uniform operands); the PTX predicate
-// `leader` restricts the instruction to one lane.  Branching on the lane in C++ instead makes the compiler wrap every
-// tcgen05 instruction in an elect/loop sequence (~80 issue cycles per MMA, measured).
+// Both helpers are executed by lane 0 of the issuing warp ONLY (the other 31 lanes skip the whole MMA role).  The
+// elect.sync with member mask 0x1 is what lets ptxas emit a bare predicated UTCHMMA: a plain `if (lane == 0)` around the
+// instruction makes it wrap every tcgen05 instruction in an elect/loop sequence (~80 issue cycles per MMA, measured),
+// while electing among 32 lanes is only correct if the warp is converged at every MMA -- lanes leaving a spin loop (or
+// a nanosleep) one by one form several convergence groups, each elects a leader and the MMA is issued more than once
+// (measured: percent-level errors).  With a single running lane there is nothing to diverge.
 __device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t leader) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
+      "elect.sync _|q, 0x1;\n\t"
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
       ::"r"(bar), "r"(leader)
       : "memory");
@@ -98,7 +123,7 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
+      "elect.sync _|q, 0x1;\n\t"
       "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
@@ -150,6 +175,7 @@ struct TcParams {
   double* dots;
   int64_t M, K, C;
   int n_parts;
+  int dbg;  // debug switches (env LOB_TC_DBG), 0 in production
 };
 
 // CP = padded column count of X (16, 32 or 48); the accumulator of one M tile is 2*CP TMEM columns.
@@ -224,35 +250,37 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // Unrolled by 6 = lcm(2 TMEM slots, 3 X stages): every TMEM address and smem descriptor below is then a
-    // loop-invariant base plus a compile-time offset.  All 32 lanes run this code; lane 0 is the issuing lane.
+    // loop-invariant base plus a compile-time offset.  Lane 0 runs the whole role alone (see umma_tf32_ts).
     static_assert(TC_NSB == 3, "the MMA issue loop is unrolled for 3 X stages");
     const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(sB));
-    const uint32_t leader = (lane == 0) ? 1u : 0u;
-    for (int kb0 = 0; kb0 < nkb; kb0 += 6) {
+    const uint32_t leader = 1u;
+    if (lane == 0) {
+      for (int kb0 = 0; kb0 < nkb; kb0 += 6) {
 #pragma unroll
-      for (int u = 0; u < 6; ++u) {
-        const int kb = kb0 + u;
-        if (kb >= nkb) break;
-        const int t = u & 1;
-        const int sb = u % 3;
-        const uint32_t pht = (kb >> 1) & 1;
-        mbar_wait(smem_u32(&tm_full[t]), pht);
-        tc_fence_after();
-        const uint64_t bdesc = bdesc0 + (uint64_t)((sb * B_STAGE) >> 4);
+        for (int u = 0; u < 6; ++u) {
+          const int kb = kb0 + u;
+          if (kb >= nkb) break;
+          const int t = u & 1;
+          const int sb = u % 3;
+          const uint32_t pht = (kb >> 1) & 1;
+          mbar_wait(smem_u32(&tm_full[t]), pht);
+          tc_fence_after();
+          const uint64_t bdesc = bdesc0 + (uint64_t)((sb * B_STAGE) >> 4);
 #pragma unroll
-        for (int tile = 0; tile < 2; ++tile) {
-          const uint32_t d_addr = tmem_base + tile * D_STRIDE;
-          const uint32_t a_hi = tmem_base + SLOT0 + t * SLOT_COLS + tile * 64;
-          const uint32_t a_lo = a_hi + 32;
+          for (int tile = 0; tile < 2; ++tile) {
+            const uint32_t d_addr = tmem_base + tile * D_STRIDE;
+            const uint32_t a_hi = tmem_base + SLOT0 + t * SLOT_COLS + tile * 64;
+            const uint32_t a_lo = a_hi + 32;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t bd = bdesc + (uint64_t)((k * 32) >> 4);  // 8 tf32 = 32 bytes inside the swizzle span
-            umma_tf32_ts(d_addr, a_hi + k * 8, bd, IDESC_WIDE, (kb | k) ? 1u : 0u, leader);
-            umma_tf32_ts(d_addr, a_lo + k * 8, bd, IDESC_NARROW, 1u, leader);
+            for (int k = 0; k < TC_BK / 8; ++k) {
+              const uint64_t bd = bdesc + (uint64_t)((k * 32) >> 4);  // 8 tf32 = 32 bytes inside the swizzle span
+              umma_tf32_ts(d_addr, a_hi + k * 8, bd, IDESC_WIDE, (kb | k) ? 1u : 0u, leader);
+              umma_tf32_ts(d_addr, a_lo + k * 8, bd, IDESC_NARROW, 1u, leader);
+            }
           }
+          umma_commit(smem_u32(&tm_empty[t]), leader);
+          if (kb == nkb - 1) umma_commit(smem_u32(acc_full), leader);
         }
-        umma_commit(smem_u32(&tm_empty[t]), leader);
-        if (kb == nkb - 1) umma_commit(smem_u32(acc_full), leader);
       }
     }
   } else if (warp < 4) {
@@ -274,12 +302,15 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
     const int C = (int)p.C;
     const int total = TC_BK * C;
     uint32_t off[NE];
-    int kk[NE];
+    int kk[NE], eidx[NE];
 #pragma unroll
     for (int i = 0; i < NE; ++i) {
-      const int e = ctid + i * 256;
+      // slots past the end of the block duplicate its last element (same address, same value): no divergent branch
+      // anywhere near the .sync.aligned TMEM instructions
+      const int e = min(ctid + i * 256, total - 1);
       const int k = e / C, c = e - k * C;
-      kk[i] = (e < total) ? k : TC_BK;  // TC_BK = never valid
+      kk[i] = k;
+      eidx[i] = e;
       off[i] = (uint32_t)c * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)c & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
     }
     float x0[NE], x1[NE];
@@ -287,9 +318,12 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
       if (kb < nkb) {
         const int64_t k1 = (int64_t)kb * TC_BK;
         const int kvalid = (int)min((int64_t)TC_BK, p.K - k1);
-        const float* src = Xb + k1 * C + ctid;
+        const float* src = Xb + k1 * C;
 #pragma unroll
-        for (int i = 0; i < NE; ++i) reg[i] = (kk[i] < kvalid) ? __ldg(src + i * 256) : 0.f;
+        for (int i = 0; i < NE; ++i) {
+          const float v = __ldg(src + ((kk[i] < kvalid) ? eidx[i] : 0));
+          reg[i] = (kk[i] < kvalid) ? v : 0.f;
+        }
       }
     };
     auto convert_block = [&](const float (&xr)[NE], int kb) {
@@ -297,7 +331,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
       const uint32_t ph = (kb / TC_NSA) & 1;
       const int t = kb & 1;
       const uint32_t pht = (kb >> 1) & 1;
-      mbar_wait(smem_u32(&full_a[s]), ph);
+      mbar_wait_warp(smem_u32(&full_a[s]), ph);
       const unsigned char* arow = sA + s * TC_A_STAGE + tile * (128 * 128) + row * 128;
       uint32_t hi[32], lo[32];
 #pragma unroll
@@ -313,27 +347,32 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&empty_a[s]));  // smem stage consumed (values are in registers)
-      // MMA(kb-2) retired: TMEM slot t is free, and so is X stage kb % 3 (last read by MMA(kb-3))
-      mbar_wait(smem_u32(&tm_empty[t]), pht ^ 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + lane_base + SLOT0 + t * SLOT_COLS + tile * 64;
-      TC_ST32(taddr, hi);
-      TC_ST32(taddr + 32, lo);
+      // X operand of this k-block, written while the TMEM slot may still be busy: stage kb % 3 was last read by
+      // MMA(kb-3), whose retirement this warp already observed when it waited on tm_empty in iteration kb-1.
+      // (Keep this block BEFORE the TMEM stores: arbitrary code between tcgen05.st and tcgen05.wait::st corrupted
+      // single rows of the A operand -- measured, see DESIGN.md.)
       unsigned char* dst = sB + (kb % TC_NSB) * B_STAGE;
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
-        if (kk[i] < TC_BK) {
-          const uint32_t hi_bits = tf32_rna(xr[i]);
-          const float xlo = xr[i] - __uint_as_float(hi_bits);
-          *reinterpret_cast<uint32_t*>(dst + off[i]) = hi_bits;
-          // rows CP.. hold X_lo; CP is a multiple of 8 so the swizzle phase (row & 7) is unchanged
-          *reinterpret_cast<uint32_t*>(dst + off[i] + CP * 128) = tf32_rna(xlo);
-        }
+        const uint32_t hi_bits = tf32_rna(xr[i]);
+        const float xlo = xr[i] - __uint_as_float(hi_bits);
+        *reinterpret_cast<uint32_t*>(dst + off[i]) = hi_bits;
+        // rows CP.. hold X_lo; CP is a multiple of 8 so the swizzle phase (row & 7) is unchanged
+        *reinterpret_cast<uint32_t*>(dst + off[i] + CP * 128) = tf32_rna(xlo);
       }
       fence_async_smem();
+      // MMA(kb-2) retired: TMEM slot t is free
+      mbar_wait_warp(smem_u32(&tm_empty[t]), pht ^ 1);
+      __syncwarp();  // tcgen05.st / wait::st below are .sync.aligned
+      tc_fence_after();
+      // A operand of this k-block
+      const uint32_t taddr = tmem_base + lane_base + SLOT0 + t * SLOT_COLS + tile * 64;
+      TC_ST32(taddr, hi);
+      TC_ST32(taddr + 32, lo);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
+      if (p.dbg & 16) __nanosleep(300);  // debug: perturb the hand-off timing
       if (lane == 0) mbar_arrive(smem_u32(&tm_full[t]));
     };
     load_x(x0, 0);
@@ -348,7 +387,8 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
     }
 
     // ---------------- epilogue ----------------
-    mbar_wait(smem_u32(acc_full), 0);
+    mbar_wait_warp(smem_u32(acc_full), 0);
+    __syncwarp();
     tc_fence_after();
     // staging (aliases the A ring, which is fully consumed): per tile xs[128][C], ys[128][C]
     float* xs = reinterpret_cast<float*>(sA) + tile * (2 * 128 * 49);
@@ -466,7 +506,8 @@ int dense_matmul_tc_f32(int64_t B, int64_t M, int64_t K, int64_t C, const float*
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return LOB_ERR_UNSUPPORTED;
   if (shared) return LOB_ERR_UNSUPPORTED;  // broadcast operator: batch coordinate would have to be pinned to 0
-  TcParams p{X, Y, d, d_bs, d_st, dots, M, K, C, (int)cdiv(M, 128)};
+  const char* dbg_env = getenv("LOB_TC_DBG");
+  TcParams p{X, Y, d, d_bs, d_st, dots, M, K, C, (int)cdiv(M, 128), dbg_env ? atoi(dbg_env) : 0};
   if (C <= 16) return launch_tc<16>(tm, p, B, st);
   if (C <= 32) return launch_tc<32>(tm, p, B, st);
   return launch_tc<48>(tm, p, B, st);

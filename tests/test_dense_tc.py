@@ -66,3 +66,19 @@ def test_dense_tc_plain_tf32_would_fail():
     Y = _kernels.dense_matmul(A, X)
     e_ours = ((Y.double() - ref).abs().max() / ref.abs().max()).item()
     assert e_ours < 3e-6 and e_ours < e_tf32 / 20
+
+
+def test_dense_tc_back_to_back_launches_are_deterministic():
+    """Six launches queued without host synchronisation must be bit-identical and accurate.  Regression test for a
+    pipeline race: lanes of the MMA-issuing warp left the mbarrier spin loop diverged, elect.sync then picked
+    different lanes for tcgen05.mma and tcgen05.commit, and the commit signalled before all MMAs had retired."""
+    A, X, d, ref = _case(4, 5000, 33, True, 11)
+    outs = []
+    for _ in range(6):
+        Y, dots, _n = _kernels.dense_matmul(A, X, d=d, want_dots=True)
+        outs.append((Y, dots))
+    torch.cuda.synchronize()
+    scale = ref.abs().max()
+    for Y, dots in outs:
+        assert torch.equal(Y, outs[0][0]) and torch.equal(dots, outs[0][1])
+        assert ((Y.double() - ref).abs().max() / scale).item() < 3e-5
