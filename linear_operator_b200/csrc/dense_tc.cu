@@ -216,7 +216,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
       mbar_init(smem_u32(&empty_a[i]), 8);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&tm_full[i]), 8);
+      mbar_init(smem_u32(&tm_full[i]), 256);  // every converter thread arrives for its own TMEM / smem stores
       mbar_init(smem_u32(&tm_empty[i]), 1);
     }
     mbar_init(smem_u32(acc_full), 1);
@@ -264,6 +264,8 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
           const int sb = u % 3;
           const uint32_t pht = (kb >> 1) & 1;
           mbar_wait(smem_u32(&tm_full[t]), pht);
+          if (p.dbg & 2) __nanosleep(500);  // debug: delay MMA issue after the hand-off (RAW test)
+          if (p.dbg & 64) { const long long tt = clock64(); while (clock64() - tt < 3000) {} }
           tc_fence_after();
           const uint64_t bdesc = bdesc0 + (uint64_t)((sb * B_STAGE) >> 4);
 #pragma unroll
@@ -275,9 +277,12 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
             for (int k = 0; k < TC_BK / 8; ++k) {
               const uint64_t bd = bdesc + (uint64_t)((k * 32) >> 4);  // 8 tf32 = 32 bytes inside the swizzle span
               umma_tf32_ts(d_addr, a_hi + k * 8, bd, IDESC_WIDE, (kb | k) ? 1u : 0u, leader);
-              umma_tf32_ts(d_addr, a_lo + k * 8, bd, IDESC_NARROW, 1u, leader);
+              if (p.dbg & 896) { const long long tt = clock64(); const int w = (p.dbg & 256) ? 100 : ((p.dbg & 128) ? 40 : 20); while (clock64() - tt < w) {} }
+              umma_tf32_ts(d_addr, a_lo + k * 8, bd, (p.dbg & 1024) ? IDESC_NARROW : IDESC_WIDE, 1u, leader);
+              if (p.dbg & 896) { const long long tt = clock64(); const int w = (p.dbg & 256) ? 100 : ((p.dbg & 128) ? 40 : 20); while (clock64() - tt < w) {} }
             }
           }
+          if (p.dbg & 8) __nanosleep(500);  // debug: delay the commit
           umma_commit(smem_u32(&tm_empty[t]), leader);
           if (kb == nkb - 1) umma_commit(smem_u32(acc_full), leader);
         }
@@ -320,10 +325,9 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
         const int kvalid = (int)min((int64_t)TC_BK, p.K - k1);
         const float* src = Xb + k1 * C;
 #pragma unroll
-        for (int i = 0; i < NE; ++i) {
-          const float v = __ldg(src + ((kk[i] < kvalid) ? eidx[i] : 0));
-          reg[i] = (kk[i] < kvalid) ? v : 0.f;
-        }
+        // raw loads only: the "k beyond K" zeroing happens when the value is consumed, two k-blocks later --
+        // touching the loaded register here would stall on the load and defeat the prefetch
+        for (int i = 0; i < NE; ++i) reg[i] = __ldg(src + ((kk[i] < kvalid) ? eidx[i] : 0));
       }
     };
     auto convert_block = [&](const float (&xr)[NE], int kb) {
@@ -352,10 +356,12 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
       // (Keep this block BEFORE the TMEM stores: arbitrary code between tcgen05.st and tcgen05.wait::st corrupted
       // single rows of the A operand -- measured, see DESIGN.md.)
       unsigned char* dst = sB + (kb % TC_NSB) * B_STAGE;
+      const int kvalid_x = (int)min((int64_t)TC_BK, p.K - (int64_t)kb * TC_BK);
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
-        const uint32_t hi_bits = tf32_rna(xr[i]);
-        const float xlo = xr[i] - __uint_as_float(hi_bits);
+        const float xv = (kk[i] < kvalid_x) ? xr[i] : 0.f;  // rows of X past K contribute zero
+        const uint32_t hi_bits = tf32_rna(xv);
+        const float xlo = xv - __uint_as_float(hi_bits);
         *reinterpret_cast<uint32_t*>(dst + off[i]) = hi_bits;
         // rows CP.. hold X_lo; CP is a multiple of 8 so the swizzle phase (row & 7) is unchanged
         *reinterpret_cast<uint32_t*>(dst + off[i] + CP * 128) = tf32_rna(xlo);
@@ -364,6 +370,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
       // MMA(kb-2) retired: TMEM slot t is free
       mbar_wait_warp(smem_u32(&tm_empty[t]), pht ^ 1);
       __syncwarp();  // tcgen05.st / wait::st below are .sync.aligned
+      if (p.dbg & 32) __nanosleep(500);  // debug: delay the TMEM overwrite (WAR test)
       tc_fence_after();
       // A operand of this k-block
       const uint32_t taddr = tmem_base + lane_base + SLOT0 + t * SLOT_COLS + tile * 64;
@@ -371,9 +378,9 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
       TC_ST32(taddr + 32, lo);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
-      __syncwarp();
       if (p.dbg & 16) __nanosleep(300);  // debug: perturb the hand-off timing
-      if (lane == 0) mbar_arrive(smem_u32(&tm_full[t]));
+      // every thread signals for itself: tcgen05.wait::st / fence::before_thread_sync order THIS thread's TMEM stores
+      mbar_arrive(smem_u32(&tm_full[t]));
     };
     load_x(x0, 0);
     load_x(x1, 1);
