@@ -69,16 +69,25 @@ def test_dense_tc_plain_tf32_would_fail():
 
 
 def test_dense_tc_back_to_back_launches_are_deterministic():
-    """Six launches queued without host synchronisation must be bit-identical and accurate.  Regression test for a
-    pipeline race: lanes of the MMA-issuing warp left the mbarrier spin loop diverged, elect.sync then picked
-    different lanes for tcgen05.mma and tcgen05.commit, and the commit signalled before all MMAs had retired."""
-    A, X, d, ref = _case(4, 5000, 33, True, 11)
-    outs = []
-    for _ in range(6):
-        Y, dots, _n = _kernels.dense_matmul(A, X, d=d, want_dots=True)
-        outs.append((Y, dots))
+    """Stress: 12 launches of a 960-CTA problem queued without host synchronisation must be bit-identical and agree
+    with the CUDA-core kernel.  Regression test for a pipeline hazard found while speeding the kernel up: variants
+    that issue tcgen05.mma within ~100 cycles of the tcgen05.st that produced their TMEM operand corrupt single rows
+    at the top of the first M tile (scripts/experimental/, DESIGN.md section "open issues"); the shipped kernel keeps
+    the slower, verified hand-off."""
+    import os
+
+    B, N, C = 48, 5000, 33
+    g = torch.Generator(device=DEV).manual_seed(5)
+    A = torch.randn(B, N, N, device=DEV, generator=g) / N**0.5
+    X = torch.randn(B, N, C, device=DEV, generator=g)
+    os.environ["LOB_DISABLE_TC"] = "1"
+    try:
+        ref = _kernels.dense_matmul(A, X)
+    finally:
+        del os.environ["LOB_DISABLE_TC"]
+    outs = [_kernels.dense_matmul(A, X) for _ in range(12)]
     torch.cuda.synchronize()
     scale = ref.abs().max()
-    for Y, dots in outs:
-        assert torch.equal(Y, outs[0][0]) and torch.equal(dots, outs[0][1])
-        assert ((Y.double() - ref).abs().max() / scale).item() < 3e-5
+    for Y in outs:
+        assert torch.equal(Y, outs[0])
+        assert int((((Y - ref).abs() / scale) > 1e-4).sum()) == 0
