@@ -250,7 +250,7 @@ def run_ours(args):
     mm_events = _kernels.PROFILE_MATMUL
     _kernels.PROFILE_MATMUL = None
     clocks = sampler.stop() if rank == 0 else None
-    mm_ms = [a.elapsed_time(b) for a, b in mm_events]
+    mm_ms = [a.elapsed_time(b) for a, b, big in mm_events if big]
 
     # the single collective of the multi-GPU path: all_gather of the per-rank results
     res = torch.stack([iq, ld], 0)

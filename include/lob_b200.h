@@ -80,8 +80,10 @@ int lob_cg_setup(const lob_cg_params* p, void* ws, const void* rhs, const void* 
  * residual norms, has_converged. */
 int lob_cg_residual_init(const lob_cg_params* p, void* ws, const void* rhs_n, const void* ax0, void* r, void* stream);
 
-/* linear_cg.py:213-215: rz = sum z*r, p = z.  z may alias r (no preconditioner). */
-int lob_cg_direction_init(const lob_cg_params* p, void* ws, const void* r, const void* z, void* pvec, void* stream);
+/* linear_cg.py:213-215: rz = sum z*r, p = z.  z may alias r (no preconditioner).  rz_partials: optional
+ * (B, n_rz_parts, C) double partial sums of r*z from a preconditioner with a fused epilogue (lob_dense_matmul_ex). */
+int lob_cg_direction_init(const lob_cg_params* p, void* ws, const void* r, const void* z, void* pvec,
+                          const double* rz_partials, int32_t n_rz_parts, void* stream);
 
 /* linear_cg.py:250-264 (+ :31 x update): alpha = rz / <p,Ap> with the eps rule and the converged mask,
  * r -= alpha Ap, x += alpha p; also accumulates <r,r> for the residual norm.
@@ -91,9 +93,10 @@ int lob_cg_step_xr(const lob_cg_params* p, void* ws, int32_t k, const void* ap, 
                    const double* pap_partials, int32_t n_parts, void* stream);
 
 /* linear_cg.py:31-46 + :298-332: beta = <r,z>_new / <r,z>_old (eps rule), p = z + beta p, residual norm / converged
- * flags, stop test, tridiagonal update.  z NULL -> z = r.  t_mat (S,B,T,T) may be NULL when n_tridiag == 0. */
+ * flags, stop test, tridiagonal update.  z NULL -> z = r.  t_mat (S,B,T,T) may be NULL when n_tridiag == 0.
+ * rz_partials as in lob_cg_direction_init (NULL: <r,z> is reduced here). */
 int lob_cg_step_p(const lob_cg_params* p, void* ws, int32_t k, const void* z, const void* r, void* pvec, void* t_mat,
-                  void* stream);
+                  const double* rz_partials, int32_t n_rz_parts, void* stream);
 
 /* copies the control words to host memory and synchronises the stream */
 int lob_cg_poll_sync(const lob_cg_params* p, void* ws, lob_cg_status* host_status, void* stream);
@@ -113,6 +116,16 @@ int32_t lob_dense_matmul_parts(int64_t M);
 int lob_dense_matmul(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A, int64_t lda,
                      int64_t a_batch_stride, const void* X, void* Y, const void* d, int64_t d_batch_stride,
                      int64_t d_stride, double* dots, void* stream);
+
+/* Generalised epilogue:  Y = alpha[b] * (A X) + d (.) E,  dots = per-row-tile partial sums of E * Y.
+ * E (B, M, C) may be NULL (then E = X, which needs M == K); alpha (one value per batch element, stride
+ * alpha_batch_stride) may be NULL (= 1).  With A = Q, X = Q^T r, E = r, alpha = -1/s, d = 1/s this is the whole
+ * precondition_closure z = (r - Q Q^T r)/s of added_diag_linear_operator.py:135-140 with <r, z> (linear_cg.py:35-36)
+ * coming out of the epilogue. */
+int lob_dense_matmul_ex(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A, int64_t lda,
+                        int64_t a_batch_stride, const void* X, void* Y, const void* E, const void* alpha,
+                        int64_t alpha_batch_stride, const void* d, int64_t d_batch_stride, int64_t d_stride,
+                        double* dots, void* stream);
 
 /* Out (B, I, J) = P^T Q with P (B, N, I), Q (B, N, J) row-major: reductions over the long dimension N
  * (Q^T r of added_diag_linear_operator.py:137, L^T L of the preconditioner build, U^T (D^-1 b) of

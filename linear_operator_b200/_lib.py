@@ -62,15 +62,20 @@ _SIGS = {
     "lob_cg_workspace_bytes": (c_size_t, [POINTER(CgParams)]),
     "lob_cg_setup": (ctypes.c_int, [POINTER(CgParams), _P, _P, _P, _P, _P, _P, _P]),
     "lob_cg_residual_init": (ctypes.c_int, [POINTER(CgParams), _P, _P, _P, _P, _P]),
-    "lob_cg_direction_init": (ctypes.c_int, [POINTER(CgParams), _P, _P, _P, _P, _P]),
+    "lob_cg_direction_init": (ctypes.c_int, [POINTER(CgParams), _P, _P, _P, _P, _P, c_int32, _P]),
     "lob_cg_step_xr": (ctypes.c_int, [POINTER(CgParams), _P, c_int32, _P, _P, _P, _P, _P, c_int32, _P]),
-    "lob_cg_step_p": (ctypes.c_int, [POINTER(CgParams), _P, c_int32, _P, _P, _P, _P, _P]),
+    "lob_cg_step_p": (ctypes.c_int, [POINTER(CgParams), _P, c_int32, _P, _P, _P, _P, _P, c_int32, _P]),
     "lob_cg_poll_sync": (ctypes.c_int, [POINTER(CgParams), _P, POINTER(CgStatus), _P]),
     "lob_cg_finish": (ctypes.c_int, [POINTER(CgParams), _P, _P, _P]),
     "lob_dense_matmul_parts": (c_int32, [c_int64]),
     "lob_dense_matmul": (
         ctypes.c_int,
         [c_int32, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, _P, _P, c_int64, c_int64, _P, _P],
+    ),
+    "lob_dense_matmul_ex": (
+        ctypes.c_int,
+        [c_int32, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64,
+         c_int64, _P, _P],
     ),
     "lob_matmul_nn": (
         ctypes.c_int,

@@ -244,13 +244,14 @@ __global__ void k_residual_flags(int64_t BC, int64_t C, int nchunks, const doubl
 // ---- rz0 = sum z*r (from partials), p = z (linear_cg.py:213-215) ------------------------------------------
 template <typename T>
 __global__ void k_direction_init(Dims d, const T* __restrict__ z, T* __restrict__ pvec,
-                                 const double* __restrict__ parts_rz, double* __restrict__ rz0, int is_f32) {
+                                 const double* __restrict__ parts_rz, int n_rz_parts, double* __restrict__ rz0,
+                                 int is_f32) {
   CG_PROLOGUE
   for (int64_t c0 = 0; c0 < d.C; c0 += CX) {
     const int64_t c = c0 + tx;
     if (c >= d.C) continue;
     if (chunk == 0 && ty == 0) {
-      double s = sum_parts(parts_rz, b, d.nchunks, d.C, c);
+      double s = sum_parts(parts_rz, b, n_rz_parts, d.C, c);
       rz0[b * d.C + c] = is_f32 ? (double)(float)s : s;
     }
     for (int64_t row = row0 + ty; row < row1; row += RY) {
@@ -316,7 +317,7 @@ __global__ void k_step_xr(Dims d, const T* __restrict__ ap, const T* __restrict_
 // ---- beta, p = z + beta p, residual norm, converged flags (linear_cg.py:31-46, :298-300) -------------------
 template <typename T>
 __global__ void k_step_p(Dims d, const T* __restrict__ z, T* __restrict__ pvec, const double* __restrict__ parts_rz,
-                         const double* __restrict__ parts_rr, const double* __restrict__ rz_old,
+                         int n_rz_parts, const double* __restrict__ parts_rr, const double* __restrict__ rz_old,
                          double* __restrict__ rz_new, double* __restrict__ beta_out, double* __restrict__ resid,
                          uint8_t* __restrict__ conv, const uint8_t* __restrict__ rhs_zero,
                          const lob_cg_status* status, double eps, double sua) {
@@ -325,7 +326,7 @@ __global__ void k_step_p(Dims d, const T* __restrict__ z, T* __restrict__ pvec, 
   for (int64_t c0 = 0; c0 < d.C; c0 += CX) {
     const int64_t c = c0 + tx;
     if (c >= d.C) continue;
-    const T rzn = (T)sum_parts(parts_rz, b, d.nchunks, d.C, c);
+    const T rzn = (T)sum_parts(parts_rz, b, n_rz_parts, d.C, c);
     const T rzo = (T)rz_old[b * d.C + c];
     const bool is_zero = rzo < (T)eps;
     const T be = is_zero ? (T)0 : (T)(rzn / rzo);
@@ -526,7 +527,7 @@ extern "C" int lob_cg_residual_init(const lob_cg_params* p, void* ws, const void
 }
 
 extern "C" int lob_cg_direction_init(const lob_cg_params* p, void* ws, const void* r, const void* z, void* pvec,
-                                     void* stream) {
+                                     const double* rz_partials, int32_t n_rz_parts, void* stream) {
   LOB_TRY(check_params(p));
   LOB_REQUIRE(ws && r && z && pvec, "lob_cg_direction_init: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -535,14 +536,20 @@ extern "C" int lob_cg_direction_init(const lob_cg_params* p, void* ws, const voi
   Launch l = make_launch(L);
   LOB_DISPATCH_DTYPE(p->dtype, {
     const double* parts = P.parts_rr;  // z aliases r: <r,z> = <r,r> already accumulated by residual_init
+    int n_rz = L.nchunks;
     if (z != r) {
-      k_dots_partials<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, (const scalar_t*)z, (const scalar_t*)r,
-                                                                 P.parts_rz, nullptr);
-      LOB_TRY(check_launch("k_dots_partials"));
-      parts = P.parts_rz;
+      if (rz_partials) {
+        parts = rz_partials;
+        n_rz = n_rz_parts;
+      } else {
+        k_dots_partials<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, (const scalar_t*)z, (const scalar_t*)r,
+                                                                   P.parts_rz, nullptr);
+        LOB_TRY(check_launch("k_dots_partials"));
+        parts = P.parts_rz;
+      }
     }
-    k_direction_init<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, (const scalar_t*)z, (scalar_t*)pvec, parts, P.rz,
-                                                                p->dtype == LOB_F32);
+    k_direction_init<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, (const scalar_t*)z, (scalar_t*)pvec, parts, n_rz,
+                                                                P.rz, p->dtype == LOB_F32);
     LOB_TRY(check_launch("k_direction_init"));
   });
   return LOB_OK;
@@ -577,7 +584,7 @@ extern "C" int lob_cg_step_xr(const lob_cg_params* p, void* ws, int32_t k, const
 }
 
 extern "C" int lob_cg_step_p(const lob_cg_params* p, void* ws, int32_t k, const void* z, const void* r, void* pvec,
-                             void* t_mat, void* stream) {
+                             void* t_mat, const double* rz_partials, int32_t n_rz_parts, void* stream) {
   LOB_TRY(check_params(p));
   LOB_REQUIRE(ws && r && pvec, "lob_cg_step_p: NULL pointer");
   LOB_REQUIRE(p->n_tridiag == 0 || t_mat, "lob_cg_step_p: t_mat is NULL but n_tridiag > 0");
@@ -588,15 +595,21 @@ extern "C" int lob_cg_step_p(const lob_cg_params* p, void* ws, int32_t k, const 
   const size_t bc = (size_t)p->B * p->C;
   LOB_DISPATCH_DTYPE(p->dtype, {
     const double* parts_rz = P.parts_rr;
+    int n_rz = L.nchunks;
     const scalar_t* zz = (const scalar_t*)r;
     if (z && z != r) {
-      k_dots_partials<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, (const scalar_t*)z, (const scalar_t*)r,
-                                                                 P.parts_rz, P.status);
-      LOB_TRY(check_launch("k_dots_partials"));
-      parts_rz = P.parts_rz;
       zz = (const scalar_t*)z;
+      if (rz_partials) {  // <r,z> came out of the preconditioner's fused epilogue
+        parts_rz = rz_partials;
+        n_rz = n_rz_parts;
+      } else {
+        k_dots_partials<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, (const scalar_t*)z, (const scalar_t*)r,
+                                                                   P.parts_rz, P.status);
+        LOB_TRY(check_launch("k_dots_partials"));
+        parts_rz = P.parts_rz;
+      }
     }
-    k_step_p<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, zz, (scalar_t*)pvec, parts_rz, P.parts_rr,
+    k_step_p<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, zz, (scalar_t*)pvec, parts_rz, n_rz, P.parts_rr,
                                                         P.rz + (size_t)(k & 1) * bc, P.rz + (size_t)((k + 1) & 1) * bc,
                                                         P.beta, P.resid, P.conv, P.rhs_zero, P.status, p->eps,
                                                         p->stop_updating_after);

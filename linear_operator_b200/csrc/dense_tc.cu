@@ -134,6 +134,9 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 struct TcParams {
   const float* X;
   float* Y;
+  const float* E;      // (B, M, C) matrix multiplied by the diagonal term and dotted with Y (NULL: X, needs M == K)
+  const float* alpha;  // per-batch scale of the product (NULL: 1)
+  int64_t alpha_bs;
   const float* dg;
   int64_t d_bs, d_st;
   double* dots;
@@ -369,8 +372,10 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
     float* Yb = p.Y + b * p.M * p.C;
     const bool need_x = (p.dg != nullptr) || (p.dots != nullptr);
     if (need_x) {
-      for (int e = ct; e < rows_valid * C; e += 128) xs[(e / C) * 49 + (e % C)] = Xb[tile_m0 * C + e];
+      const float* Eb = p.E ? p.E + b * p.M * p.C : Xb;
+      for (int e = ct; e < rows_valid * C; e += 128) xs[(e / C) * 49 + (e % C)] = Eb[tile_m0 * C + e];
     }
+    const float alpha_b = p.alpha ? p.alpha[b * p.alpha_bs] : 1.0f;
     // named barrier per tile (ids 1, 2), 128 threads
     asm volatile("bar.sync %0, 128;" ::"r"(1 + tile) : "memory");
     float dv = 0.f;
@@ -386,7 +391,7 @@ k_dense_tc(const __grid_constant__ CUtensorMap tmA, TcParams p) {
       for (int i = 0; i < 16; ++i) {
         const int c = c0 + i;
         if (c < C && row < rows_valid) {
-          float y = __uint_as_float(a[i]) + __uint_as_float(bb[i]);
+          float y = (__uint_as_float(a[i]) + __uint_as_float(bb[i])) * alpha_b;
           if (p.dg) y += dv * xs[row * 49 + c];
           ys[row * 49 + c] = y;
         }
@@ -458,9 +463,9 @@ static int launch_tc(const CUtensorMap& tm, const TcParams& p, int64_t B, cudaSt
 
 // returns LOB_ERR_UNSUPPORTED when the shape does not qualify (caller falls back to the CUDA-core kernel)
 int dense_matmul_tc_f32(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
-                        const float* X, float* Y, const float* d, int64_t d_bs, int64_t d_st, double* dots,
-                        cudaStream_t st) {
-  if (C > 48 || M < 128 || K < 32) return LOB_ERR_UNSUPPORTED;
+                        const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs, const float* d,
+                        int64_t d_bs, int64_t d_st, double* dots, cudaStream_t st) {
+  if (C > 48 || M < 32 || K < 32) return LOB_ERR_UNSUPPORTED;
   if ((lda % 4) != 0 || (a_bs % 4) != 0 || (reinterpret_cast<uintptr_t>(A) & 15) != 0) return LOB_ERR_UNSUPPORTED;
   if (M >= (1LL << 31) || K >= (1LL << 31)) return LOB_ERR_UNSUPPORTED;
   PFN_encodeTiled enc = get_encode_fn();
@@ -476,7 +481,7 @@ int dense_matmul_tc_f32(int64_t B, int64_t M, int64_t K, int64_t C, const float*
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return LOB_ERR_UNSUPPORTED;
   if (shared) return LOB_ERR_UNSUPPORTED;  // broadcast operator: batch coordinate would have to be pinned to 0
-  TcParams p{X, Y, d, d_bs, d_st, dots, M, K, C, (int)cdiv(M, 128)};
+  TcParams p{X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, M, K, C, (int)cdiv(M, 128)};
   if (C <= 16) return launch_tc<16>(tm, p, B, st);
   if (C <= 32) return launch_tc<32>(tm, p, B, st);
   return launch_tc<48>(tm, p, B, st);

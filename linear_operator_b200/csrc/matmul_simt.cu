@@ -21,7 +21,8 @@ template <typename T, int RN>
 __global__ void __launch_bounds__(256)
 k_matmul_nn(int64_t M, int64_t K, int64_t C, const T* __restrict__ A, int64_t lda, int64_t a_bs,
             const T* __restrict__ X, int64_t x_bs, T* __restrict__ Y, const T* __restrict__ dg, int64_t d_bs,
-            int64_t d_st, double* __restrict__ dots, int n_parts, T beta_y) {
+            int64_t d_st, double* __restrict__ dots, int n_parts, T beta_y, const T* __restrict__ E,
+            const T* __restrict__ alpha, int64_t alpha_bs) {
   constexpr int TK = TileK<T>::value;
   constexpr int CP = 8 * RN;
   __shared__ __align__(16) T As[TK * LDA_S];
@@ -95,8 +96,9 @@ k_matmul_nn(int64_t M, int64_t K, int64_t C, const T* __restrict__ A, int64_t ld
       if (cc >= ncol) continue;
       const int64_t idx = row * C + c0 + cc;
       T y = acc[i][j];
+      if (alpha) y *= alpha[b * alpha_bs];
       T xv = (T)0;
-      if (dg || dots) xv = Xb[idx];  // requires M == K
+      if (dg || dots) xv = E ? E[b * M * C + idx] : Xb[idx];  // E == NULL requires M == K
       if (dg) y += dv * xv;
       if (beta_y != (T)0) y += beta_y * Yb[idx];
       Yb[idx] = y;
@@ -190,7 +192,7 @@ __global__ void k_reduce_splits(int64_t total_per_batch, int nsplit, const ACC* 
 template <typename T>
 static int launch_nn(int64_t B, int64_t M, int64_t K, int64_t C, const T* A, int64_t lda, int64_t a_bs, const T* X,
                      int64_t x_bs, T* Y, const T* d, int64_t d_bs, int64_t d_st, double* dots, double beta_y,
-                     cudaStream_t st) {
+                     cudaStream_t st, const T* E = nullptr, const T* alpha = nullptr, int64_t alpha_bs = 0) {
   const int rn = pick_rn(C);
   const int cp = 8 * rn;
   dim3 grid((unsigned)cdiv(M, TM), (unsigned)B, (unsigned)cdiv(C, cp));
@@ -198,7 +200,7 @@ static int launch_nn(int64_t B, int64_t M, int64_t K, int64_t C, const T* A, int
 #define LOB_NN_CASE(R)                                                                                          \
   case R:                                                                                                       \
     k_matmul_nn<T, R><<<grid, 256, 0, st>>>(M, K, C, A, lda, a_bs, X, x_bs, Y, d, d_bs, d_st, dots, n_parts,      \
-                                            (T)beta_y);                                                         \
+                                            (T)beta_y, E, alpha, alpha_bs);                                     \
     break;
   switch (rn) {
     LOB_NN_CASE(1) LOB_NN_CASE(2) LOB_NN_CASE(3) LOB_NN_CASE(4) LOB_NN_CASE(5) LOB_NN_CASE(6) LOB_NN_CASE(7)
@@ -270,8 +272,29 @@ extern "C" int lob_matmul_nn(int32_t dtype, int64_t B, int64_t M, int64_t K, int
 
 namespace lob {
 int dense_matmul_tc_f32(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
-                        const float* X, float* Y, const float* d, int64_t d_bs, int64_t d_st, double* dots,
-                        cudaStream_t st);
+                        const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs, const float* d,
+                        int64_t d_bs, int64_t d_st, double* dots, cudaStream_t st);
+}
+
+extern "C" int lob_dense_matmul_ex(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A,
+                                   int64_t lda, int64_t a_batch_stride, const void* X, void* Y, const void* E,
+                                   const void* alpha, int64_t alpha_batch_stride, const void* d,
+                                   int64_t d_batch_stride, int64_t d_stride, double* dots, void* stream) {
+  LOB_REQUIRE(B > 0 && M > 0 && K > 0 && C > 0, "lob_dense_matmul_ex: sizes must be positive");
+  LOB_REQUIRE(B <= 65535, "lob_dense_matmul_ex: flattened batch > 65535 not supported");
+  LOB_REQUIRE(A && X && Y, "lob_dense_matmul_ex: NULL pointer");
+  LOB_REQUIRE((!d && !dots) || E || M == K, "lob_dense_matmul_ex: diagonal / dots need E or a square operator");
+  if (dtype == LOB_F32 && !getenv("LOB_DISABLE_TC")) {
+    int s = dense_matmul_tc_f32(B, M, K, C, (const float*)A, lda, a_batch_stride, (const float*)X, (float*)Y,
+                                (const float*)E, (const float*)alpha, alpha_batch_stride, (const float*)d,
+                                d_batch_stride, d_stride, dots, (cudaStream_t)stream);
+    if (s != LOB_ERR_UNSUPPORTED) return s;
+  }
+  LOB_DISPATCH_DTYPE(dtype, {
+    return launch_nn<scalar_t>(B, M, K, C, (const scalar_t*)A, lda, a_batch_stride, (const scalar_t*)X, K * C,
+                               (scalar_t*)Y, (const scalar_t*)d, d_batch_stride, d_stride, dots, 0.0,
+                               (cudaStream_t)stream, (const scalar_t*)E, (const scalar_t*)alpha, alpha_batch_stride);
+  });
 }
 
 extern "C" int lob_dense_matmul(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A, int64_t lda,
@@ -283,8 +306,8 @@ extern "C" int lob_dense_matmul(int32_t dtype, int64_t B, int64_t M, int64_t K, 
   LOB_REQUIRE((!d && !dots) || M == K, "lob_dense_matmul: fused diagonal / dots need a square operator");
   if (dtype == LOB_F32 && !getenv("LOB_DISABLE_TC")) {
     // tensor-core path (dense_tc.cu); shapes it does not cover fall through to the CUDA-core kernel
-    int s = dense_matmul_tc_f32(B, M, K, C, (const float*)A, lda, a_batch_stride, (const float*)X, (float*)Y,
-                                (const float*)d, d_batch_stride, d_stride, dots, (cudaStream_t)stream);
+    int s = dense_matmul_tc_f32(B, M, K, C, (const float*)A, lda, a_batch_stride, (const float*)X, (float*)Y, nullptr,
+                                nullptr, 0, (const float*)d, d_batch_stride, d_stride, dots, (cudaStream_t)stream);
     if (s != LOB_ERR_UNSUPPORTED) return s;
   }
   LOB_DISPATCH_DTYPE(dtype, {

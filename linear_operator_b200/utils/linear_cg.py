@@ -158,9 +158,22 @@ def linear_cg(
     if have_guess:
         poll()  # the reference checks for NaNs right here (:199); with a user guess we keep that timing
 
-    z = preconditioner(r).contiguous() if precond else r  # :213
+    precond_fused = getattr(preconditioner, "fused", None) if precond else None
+
+    def apply_precond(res):
+        """z = M^-1 r (:213,:268); preconditioners with a fused epilogue also hand back the <r, z> partial sums"""
+        if precond_fused is not None:
+            zz, rz_parts, n_rz = precond_fused(res)
+            return zz.contiguous(), rz_parts, n_rz
+        return preconditioner(res).contiguous(), None, 0
+
+    if precond:
+        z, rz_parts, n_rz = apply_precond(r)
+    else:
+        z, rz_parts, n_rz = r, None, 0
     pvec = torch.empty_like(r)
-    check(lib.lob_cg_direction_init(ctypes_byref(p), ptr(ws), ptr(r), ptr(z), ptr(pvec), st), "lob_cg_direction_init")
+    check(lib.lob_cg_direction_init(ctypes_byref(p), ptr(ws), ptr(r), ptr(z), ptr(pvec), ptr(rz_parts), n_rz, st),
+          "lob_cg_direction_init")
 
     # first iteration index at which the reference's stop rule (:302-306) can fire
     first_stop = min(10, max_iter - 1)
@@ -181,9 +194,12 @@ def linear_cg(
         ap = ap.contiguous()
         check(lib.lob_cg_step_xr(ctypes_byref(p), ptr(ws), k, ptr(ap), ptr(pvec), ptr(x), ptr(r), ptr(dots), n_parts,
                                  st), "lob_cg_step_xr")
-        z = preconditioner(r).contiguous() if precond else None  # :268
-        check(lib.lob_cg_step_p(ctypes_byref(p), ptr(ws), k, ptr(z), ptr(r), ptr(pvec), ptr(t_mat), st),
-              "lob_cg_step_p")
+        if precond:
+            z, rz_parts, n_rz = apply_precond(r)
+        else:
+            z, rz_parts, n_rz = None, None, 0
+        check(lib.lob_cg_step_p(ctypes_byref(p), ptr(ws), k, ptr(z), ptr(r), ptr(pvec), ptr(t_mat), ptr(rz_parts), n_rz,
+                                st), "lob_cg_step_p")
         polled = False
         if k == 0 or k >= first_stop or k == n_iter - 1:
             polled = True

@@ -91,3 +91,28 @@ def test_dense_tc_back_to_back_launches_are_deterministic():
     for Y in outs:
         assert torch.equal(Y, outs[0])
         assert int((((Y - ref).abs() / scale) > 1e-4).sum()) == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("constant_diag", [True, False])
+def test_dense_matmul_generalised_epilogue(dtype, constant_diag):
+    """Y = alpha[b] (A X) + d (.) E and the partial sums of E * Y -- the fused precondition_closure form
+    (A = Q, X = Q^T r, E = r).  fp32 goes through the tensor-core kernel (K = 100), fp64 through the CUDA-core one."""
+    B, N, k, C = 3, 1000, 100, 33
+    g = torch.Generator(device=DEV).manual_seed(3)
+    Q = torch.randn(B, N, k, device=DEV, generator=g, dtype=dtype) / N**0.5
+    t = torch.randn(B, k, C, device=DEV, generator=g, dtype=dtype)
+    E = torch.randn(B, N, C, device=DEV, generator=g, dtype=dtype)
+    alpha = -(0.5 + torch.rand(B, device=DEV, generator=g, dtype=dtype))
+    d = (0.5 + torch.rand(B, 1 if constant_diag else N, device=DEV, generator=g, dtype=dtype))
+    Y, dots, _n = _kernels.dense_matmul(Q, t, d=d, want_dots=True, E=E, alpha=alpha)
+    ref = alpha.double().view(B, 1, 1) * (Q.double() @ t.double()) + d.double().expand(B, N).unsqueeze(-1) * E.double()
+    tol = 1e-5 if dtype == torch.float32 else 1e-13
+    assert ((Y.double() - ref).abs().max() / ref.abs().max()).item() < tol
+    dref = (E.double() * ref).sum(-2)
+    assert ((dots.sum(1) - dref).abs().max() / dref.abs().max()).item() < tol
+    # skinny output (M < 128): t = Q^T r through the same kernel
+    Qt = Q.mT.contiguous()
+    T2 = _kernels.dense_matmul(Qt, E)
+    ref2 = Qt.double() @ E.double()
+    assert ((T2.double() - ref2).abs().max() / ref2.abs().max()).item() < tol
