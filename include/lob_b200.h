@@ -113,9 +113,13 @@ int lob_cg_finish(const lob_cg_params* p, void* ws, void* x, void* stream);
  * row tiles: the <p, A p> reduction of linear_cg.py:250-251 fused into the matmul epilogue.
  * ---------------------------------------------------------------------------------------------------------- */
 int32_t lob_dense_matmul_parts(int64_t M);
+/* Scratch for the streaming tensor-core kernel (dense_stream.cu): the tf32 split of X^T, (B, R(C), K) floats.
+ * 0 when the shape / dtype is served by a kernel that needs none.  ws may be NULL (or too small): the call then runs
+ * on the slower workspace-free CUDA kernels. */
+size_t lob_dense_matmul_workspace_bytes(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C);
 int lob_dense_matmul(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A, int64_t lda,
                      int64_t a_batch_stride, const void* X, void* Y, const void* d, int64_t d_batch_stride,
-                     int64_t d_stride, double* dots, void* stream);
+                     int64_t d_stride, double* dots, void* ws, size_t ws_bytes, void* stream);
 
 /* Generalised epilogue:  Y = alpha[b] * (A X) + d (.) E,  dots = per-row-tile partial sums of E * Y.
  * E (B, M, C) may be NULL (then E = X, which needs M == K); alpha (one value per batch element, stride
@@ -125,7 +129,7 @@ int lob_dense_matmul(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, 
 int lob_dense_matmul_ex(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A, int64_t lda,
                         int64_t a_batch_stride, const void* X, void* Y, const void* E, const void* alpha,
                         int64_t alpha_batch_stride, const void* d, int64_t d_batch_stride, int64_t d_stride,
-                        double* dots, void* stream);
+                        double* dots, void* ws, size_t ws_bytes, void* stream);
 
 /* Out (B, I, J) = P^T Q with P (B, N, I), Q (B, N, J) row-major: reductions over the long dimension N
  * (Q^T r of added_diag_linear_operator.py:137, L^T L of the preconditioner build, U^T (D^-1 b) of

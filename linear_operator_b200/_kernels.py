@@ -76,6 +76,9 @@ def dense_matmul(A: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = N
     n_parts = int(lib.lob_dense_matmul_parts(M))
     if want_dots:
         dots = torch.empty(B, n_parts, C, dtype=torch.float64, device=X.device)
+    # scratch of the streaming tensor-core kernel (tf32 split of X^T); torch's caching allocator makes this free
+    ws_bytes = int(lib.lob_dense_matmul_workspace_bytes(dt(X), B, M, K, C))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device) if ws_bytes else None
     prof = PROFILE_MATMUL
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -83,7 +86,7 @@ def dense_matmul(A: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = N
     if E is None and alpha is None:
         check(
             lib.lob_dense_matmul(dt(X), B, M, K, C, ptr(Af), lda, a_bs, ptr(Xf), ptr(Y), ptr(dd), d_bs, d_st,
-                                 ptr(dots), stream(X)),
+                                 ptr(dots), ptr(ws), ws_bytes, stream(X)),
             "lob_dense_matmul",
         )
     else:
@@ -92,7 +95,7 @@ def dense_matmul(A: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = N
         check(
             lib.lob_dense_matmul_ex(dt(X), B, M, K, C, ptr(Af), lda, a_bs, ptr(Xf), ptr(Y), ptr(Ef), ptr(al),
                                     0 if (al is None or al.numel() == 1) else 1, ptr(dd), d_bs, d_st, ptr(dots),
-                                    stream(X)),
+                                    ptr(ws), ws_bytes, stream(X)),
             "lob_dense_matmul_ex",
         )
     if prof is not None:

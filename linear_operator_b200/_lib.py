@@ -68,14 +68,16 @@ _SIGS = {
     "lob_cg_poll_sync": (ctypes.c_int, [POINTER(CgParams), _P, POINTER(CgStatus), _P]),
     "lob_cg_finish": (ctypes.c_int, [POINTER(CgParams), _P, _P, _P]),
     "lob_dense_matmul_parts": (c_int32, [c_int64]),
+    "lob_dense_matmul_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64, c_int64, c_int64]),
     "lob_dense_matmul": (
         ctypes.c_int,
-        [c_int32, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, _P, _P, c_int64, c_int64, _P, _P],
+        [c_int32, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, _P, _P, c_int64, c_int64, _P, _P,
+         c_size_t, _P],
     ),
     "lob_dense_matmul_ex": (
         ctypes.c_int,
         [c_int32, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64,
-         c_int64, _P, _P],
+         c_int64, _P, _P, c_size_t, _P],
     ),
     "lob_matmul_nn": (
         ctypes.c_int,

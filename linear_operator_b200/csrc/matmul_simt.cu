@@ -11,6 +11,9 @@
 // words of B per 4*RN FMAs.
 #include <stdlib.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "simt_tile.cuh"
 
@@ -274,20 +277,51 @@ namespace lob {
 int dense_matmul_tc_f32(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
                         const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs, const float* d,
                         int64_t d_bs, int64_t d_st, double* dots, cudaStream_t st);
+size_t dense_stream_workspace_bytes(int64_t B, int64_t K, int64_t C);
+int dense_matmul_stream_f32(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
+                            const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
+                            const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
+                            cudaStream_t st);
+
+// fp32 dispatch: streaming tcgen05 kernel (needs the workspace) -> first-generation tcgen05 kernel -> CUDA cores.
+// LOB_DENSE_IMPL = stream | tc | simt pins one of them (diagnostics, A/B comparisons).
+static int dense_f32_tensor_paths(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
+                                  const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
+                                  const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
+                                  cudaStream_t st) {
+  const char* impl = getenv("LOB_DENSE_IMPL");
+  if (getenv("LOB_DISABLE_TC") || (impl && !strcmp(impl, "simt"))) return LOB_ERR_UNSUPPORTED;
+  // Short contractions (the K = rank preconditioner product Q t) are per-tile-overhead bound in the persistent kernel
+  // (few k-blocks per 256-row tile, epilogue not hidden): they stay on the first-generation kernel unless pinned.
+  const bool pinned_stream = impl && !strcmp(impl, "stream");
+  if (pinned_stream || (!impl && K >= 512)) {
+    int s = dense_matmul_stream_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, ws,
+                                    ws_bytes, st);
+    if (s != LOB_ERR_UNSUPPORTED) return s;
+  }
+  return dense_matmul_tc_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, st);
+}
+}
+
+extern "C" size_t lob_dense_matmul_workspace_bytes(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C) {
+  (void)M;
+  if (dtype != LOB_F32) return 0;
+  return lob::dense_stream_workspace_bytes(B, K, C);
 }
 
 extern "C" int lob_dense_matmul_ex(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A,
                                    int64_t lda, int64_t a_batch_stride, const void* X, void* Y, const void* E,
                                    const void* alpha, int64_t alpha_batch_stride, const void* d,
-                                   int64_t d_batch_stride, int64_t d_stride, double* dots, void* stream) {
+                                   int64_t d_batch_stride, int64_t d_stride, double* dots, void* ws, size_t ws_bytes,
+                                   void* stream) {
   LOB_REQUIRE(B > 0 && M > 0 && K > 0 && C > 0, "lob_dense_matmul_ex: sizes must be positive");
   LOB_REQUIRE(B <= 65535, "lob_dense_matmul_ex: flattened batch > 65535 not supported");
   LOB_REQUIRE(A && X && Y, "lob_dense_matmul_ex: NULL pointer");
   LOB_REQUIRE((!d && !dots) || E || M == K, "lob_dense_matmul_ex: diagonal / dots need E or a square operator");
-  if (dtype == LOB_F32 && !getenv("LOB_DISABLE_TC")) {
-    int s = dense_matmul_tc_f32(B, M, K, C, (const float*)A, lda, a_batch_stride, (const float*)X, (float*)Y,
-                                (const float*)E, (const float*)alpha, alpha_batch_stride, (const float*)d,
-                                d_batch_stride, d_stride, dots, (cudaStream_t)stream);
+  if (dtype == LOB_F32) {
+    int s = dense_f32_tensor_paths(B, M, K, C, (const float*)A, lda, a_batch_stride, (const float*)X, (float*)Y,
+                                   (const float*)E, (const float*)alpha, alpha_batch_stride, (const float*)d,
+                                   d_batch_stride, d_stride, dots, ws, ws_bytes, (cudaStream_t)stream);
     if (s != LOB_ERR_UNSUPPORTED) return s;
   }
   LOB_DISPATCH_DTYPE(dtype, {
@@ -299,15 +333,16 @@ extern "C" int lob_dense_matmul_ex(int32_t dtype, int64_t B, int64_t M, int64_t 
 
 extern "C" int lob_dense_matmul(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A, int64_t lda,
                                 int64_t a_batch_stride, const void* X, void* Y, const void* d, int64_t d_batch_stride,
-                                int64_t d_stride, double* dots, void* stream) {
+                                int64_t d_stride, double* dots, void* ws, size_t ws_bytes, void* stream) {
   LOB_REQUIRE(B > 0 && M > 0 && K > 0 && C > 0, "lob_dense_matmul: sizes must be positive");
   LOB_REQUIRE(B <= 65535, "lob_dense_matmul: flattened batch > 65535 not supported");
   LOB_REQUIRE(A && X && Y, "lob_dense_matmul: NULL pointer");
   LOB_REQUIRE((!d && !dots) || M == K, "lob_dense_matmul: fused diagonal / dots need a square operator");
-  if (dtype == LOB_F32 && !getenv("LOB_DISABLE_TC")) {
-    // tensor-core path (dense_tc.cu); shapes it does not cover fall through to the CUDA-core kernel
-    int s = dense_matmul_tc_f32(B, M, K, C, (const float*)A, lda, a_batch_stride, (const float*)X, (float*)Y, nullptr,
-                                nullptr, 0, (const float*)d, d_batch_stride, d_stride, dots, (cudaStream_t)stream);
+  if (dtype == LOB_F32) {
+    // tensor-core paths (dense_stream.cu, dense_tc.cu); shapes they do not cover fall through to the CUDA-core kernel
+    int s = dense_f32_tensor_paths(B, M, K, C, (const float*)A, lda, a_batch_stride, (const float*)X, (float*)Y,
+                                   nullptr, nullptr, 0, (const float*)d, d_batch_stride, d_stride, dots, ws, ws_bytes,
+                                   (cudaStream_t)stream);
     if (s != LOB_ERR_UNSUPPORTED) return s;
   }
   LOB_DISPATCH_DTYPE(dtype, {

@@ -1,0 +1,375 @@
+// Standalone harness for k_dense_stream (dense_stream.cu): correctness against an fp64 host product over a grid of
+// shapes / configurations, a check of how the tensor core converts fp32 -> tf32, bit-for-bit repeatability under load,
+// and a throughput sweep at the BASELINE config-2 tile shape.  Build:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Iinclude -Ilinear_operator_b200/csrc \
+//        scripts/dense_stream_harness.cu linear_operator_b200/csrc/dense_stream.cu linear_operator_b200/csrc/api.cu \
+//        -o scripts/dense_stream_harness
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "lob_b200.h"
+
+namespace lob {
+struct DsConfig {
+  int bk, sa, sl, lo_mode, grid, dbg;
+};
+size_t dense_stream_workspace_bytes(int64_t B, int64_t K, int64_t C);
+int dense_matmul_stream_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
+                                const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
+                                const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
+                                cudaStream_t st, DsConfig cfg);
+}  // namespace lob
+
+#define CK(x)                                                                        \
+  do {                                                                               \
+    cudaError_t e_ = (x);                                                            \
+    if (e_ != cudaSuccess) {                                                         \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                       \
+    }                                                                                \
+  } while (0)
+
+__host__ __device__ inline uint32_t hash32(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return (uint32_t)x;
+}
+__host__ __device__ inline float rnd(uint64_t seed, uint64_t i) {
+  return ((float)(hash32(seed * 0x9E3779B97F4A7C15ULL + i) >> 8) + 0.5f) * (2.0f / 16777216.0f) - 1.0f;
+}
+static bool g_positive = false;  // all-positive data: exposes accumulation bias (no cancellation)
+__global__ void k_fill(float* p, size_t n, uint64_t seed, float scale, bool positive) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = rnd(seed, i) * scale;
+    p[i] = positive ? fabsf(v) : v;
+  }
+}
+static inline float hval(uint64_t seed, uint64_t i) {
+  const float v = rnd(seed, i);
+  return g_positive ? fabsf(v) : v;
+}
+
+static float* dalloc_fill(size_t n, uint64_t seed, float scale = 1.f) {
+  float* p;
+  CK(cudaMalloc(&p, n * sizeof(float)));
+  k_fill<<<1184, 256>>>(p, n, seed, scale, g_positive);
+  CK(cudaGetLastError());
+  return p;
+}
+
+static inline float trunc_tf32(float a) {
+  uint32_t u;
+  memcpy(&u, &a, 4);
+  u &= 0xFFFFE000u;
+  memcpy(&a, &u, 4);
+  return a;
+}
+static inline float rna_tf32(float a) {
+  uint32_t u;
+  memcpy(&u, &a, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&a, &u, 4);
+  return a;
+}
+
+struct Case {
+  int64_t B, M, K, C;
+  bool diag, dots, ex;  // ex: separate E + alpha (the preconditioner epilogue)
+  bool const_diag;
+};
+
+// returns max normalised error  |y - y_ref| / (sum_k |a||x| + |d e|)  over sampled rows
+static double run_case(const Case& cs, lob::DsConfig cfg, int nsample_rows, double* dots_err, int* status,
+                       double* model_err = nullptr) {
+  const int64_t B = cs.B, M = cs.M, K = cs.K, C = cs.C;
+  float* A = dalloc_fill((size_t)B * M * K, 11);
+  float* X = dalloc_fill((size_t)B * K * C, 22);
+  float* E = cs.ex ? dalloc_fill((size_t)B * M * C, 33) : nullptr;
+  float* al = cs.ex ? dalloc_fill((size_t)B, 44) : nullptr;
+  const int64_t dn = cs.const_diag ? 1 : M;
+  float* d = cs.diag ? dalloc_fill((size_t)B * dn, 55) : nullptr;
+  float* Y;
+  CK(cudaMalloc(&Y, (size_t)B * M * C * 4));
+  CK(cudaMemset(Y, 0xFF, (size_t)B * M * C * 4));
+  const int n_parts = (int)((M + 127) / 128);
+  double* dots = nullptr;
+  if (cs.dots) {
+    CK(cudaMalloc(&dots, (size_t)B * n_parts * C * 8));
+    CK(cudaMemset(dots, 0xFF, (size_t)B * n_parts * C * 8));
+  }
+  const size_t wsb = lob::dense_stream_workspace_bytes(B, K, C);
+  void* ws;
+  CK(cudaMalloc(&ws, wsb));
+  int s = lob::dense_matmul_stream_f32_cfg(B, M, K, C, A, K, M * K, X, Y, E, al, 1, d, dn, cs.const_diag ? 0 : 1, dots,
+                                           ws, wsb, 0, cfg);
+  *status = s;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (s != 0 || e != cudaSuccess) {
+    printf("   launch status %d (%s) cuda %s\n", s, lob_last_error(), cudaGetErrorString(e));
+    if (e != cudaSuccess) exit(3);
+    return 1e30;
+  }
+  std::vector<float> hY((size_t)B * M * C);
+  CK(cudaMemcpy(hY.data(), Y, hY.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<double> hdots;
+  if (cs.dots) {
+    hdots.resize((size_t)B * n_parts * C);
+    CK(cudaMemcpy(hdots.data(), dots, hdots.size() * 8, cudaMemcpyDeviceToHost));
+  }
+  // host reference on sampled rows (all rows when small)
+  double worst = 0.0;
+  double worst_trunc = 0.0, worst_rna = 0.0;
+  std::vector<int64_t> rows;
+  if (M <= nsample_rows) {
+    for (int64_t r = 0; r < M; ++r) rows.push_back(r);
+  } else {
+    for (int i = 0; i < nsample_rows; ++i) rows.push_back((int64_t)(hash32(777 + i) % M));
+    rows.push_back(0);
+    rows.push_back(M - 1);
+    rows.push_back(std::min<int64_t>(M - 1, 127));
+    rows.push_back(std::min<int64_t>(M - 1, 128));
+    rows.push_back(std::min<int64_t>(M - 1, 255));
+    rows.push_back(std::min<int64_t>(M - 1, 256));
+  }
+  std::vector<double> xcol((size_t)K * C);
+  for (int64_t b = 0; b < B; ++b) {
+    for (int64_t k = 0; k < K; ++k)
+      for (int64_t c = 0; c < C; ++c) xcol[k * C + c] = hval(22, (uint64_t)((b * K + k) * C + c));
+    for (int64_t r : rows) {
+      for (int64_t c = 0; c < C; ++c) {
+        double acc = 0, accabs = 0, acc_t = 0, acc_r = 0;
+        for (int64_t k = 0; k < K; ++k) {
+          const float a = hval(11, (uint64_t)((b * M + r) * K + k));
+          const double x = xcol[k * C + c];
+          acc += (double)a * x;
+          accabs += fabs((double)a * x);
+          if (model_err) {
+            acc_t += (double)trunc_tf32(a) * x;
+            acc_r += (double)rna_tf32(a) * x;
+          }
+        }
+        const double alpha = cs.ex ? (double)(hval(44, (uint64_t)b)) : 1.0;
+        double ref = alpha * acc;
+        double ev = 0.0;
+        if (cs.diag || cs.dots) ev = cs.ex ? (double)hval(33, (uint64_t)((b * M + r) * C + c)) : xcol[r * C + c];
+        if (cs.diag) {
+          const double dv = hval(55, (uint64_t)(b * dn + (cs.const_diag ? 0 : r)));
+          ref += dv * ev;
+          accabs += fabs(dv * ev);
+        }
+        const double got = hY[(size_t)(b * M + r) * C + c];
+        const double err = fabs(got - ref) / (accabs + 1e-30);
+        if (!(err <= worst)) worst = err;  // NaN-propagating max
+        if (model_err) {
+          worst_trunc = std::max(worst_trunc, fabs(got - acc_t) / (accabs + 1e-30));
+          worst_rna = std::max(worst_rna, fabs(got - acc_r) / (accabs + 1e-30));
+        }
+      }
+    }
+  }
+  if (model_err) {
+    model_err[0] = worst_trunc;
+    model_err[1] = worst_rna;
+  }
+  // dots: compare with the dot of E and the GPU's own Y (exact in double up to summation order)
+  *dots_err = 0.0;
+  if (cs.dots) {
+    for (int64_t b = 0; b < B; ++b)
+      for (int pi = 0; pi < n_parts; ++pi)
+        for (int64_t c = 0; c < C; ++c) {
+          double sref = 0, sabs = 0;
+          for (int64_t r = (int64_t)pi * 128; r < std::min<int64_t>(M, (int64_t)(pi + 1) * 128); ++r) {
+            const double ev = cs.ex ? (double)hval(33, (uint64_t)((b * M + r) * C + c))
+                                    : (double)hval(22, (uint64_t)((b * K + r) * C + c));
+            const double yv = hY[(size_t)(b * M + r) * C + c];
+            sref += ev * yv;
+            sabs += fabs(ev * yv);
+          }
+          const double got = hdots[(size_t)(b * n_parts + pi) * C + c];
+          const double err = fabs(got - sref) / (sabs + 1e-30);
+          if (!(err <= *dots_err)) *dots_err = err;
+        }
+  }
+  // untouched-output check: Y was memset to NaN bit patterns, every entry must have been written
+  size_t nan_cnt = 0;
+  for (float v : hY)
+    if (v != v) ++nan_cnt;
+  if (nan_cnt) {
+    printf("   %zu unwritten / NaN outputs\n", nan_cnt);
+    worst = 1e30;
+  }
+  cudaFree(A);
+  cudaFree(X);
+  if (E) cudaFree(E);
+  if (al) cudaFree(al);
+  if (d) cudaFree(d);
+  cudaFree(Y);
+  if (dots) cudaFree(dots);
+  cudaFree(ws);
+  return worst;
+}
+
+int main(int argc, char** argv) {
+  int perfB = argc > 1 ? atoi(argv[1]) : 256;
+  int perfN = argc > 2 ? atoi(argv[2]) : 5000;
+  int reps = argc > 3 ? atoi(argv[3]) : 5;
+  const bool perf_only = argc > 4 && strcmp(argv[4], "perfonly") == 0;
+  int failures = 0;
+  if (!perf_only) {
+
+  // ---------------- 1. fp32 -> tf32 conversion model of the tensor core ----------------
+  for (int bk : {16, 32}) {
+    Case cs{1, 256, 512, 16, false, false, false, false};
+    double de, me[2];
+    int st;
+    lob::DsConfig cfg{bk, 0, 0, 2, 0, 0};
+    double err = run_case(cs, cfg, 1 << 30, &de, &st, me);
+    printf("[model] BK=%d lo disabled: err vs exact %.3e | vs trunc(A) model %.3e | vs rna(A) model %.3e\n", bk, err,
+           me[0], me[1]);
+  }
+  // ---------------- 1b. accumulation bias on all-positive data (no cancellation) ----------------
+  for (int64_t K : {512, 2048, 5000}) {
+    g_positive = true;
+    Case cs{1, 256, K, 16, false, false, false, false};
+    double de;
+    int st;
+    lob::DsConfig cfg{16, 0, 0, 0, 0, 0};
+    const double err = run_case(cs, cfg, 64, &de, &st);
+    printf("[bias] all-positive data K=%lld: normalised err %.3e\n", (long long)K, err);
+    g_positive = false;
+  }
+  // ---------------- 2. correctness grid ----------------
+  const Case cases[] = {
+      {1, 256, 512, 16, false, false, false, false},   {2, 700, 700, 33, true, true, false, false},
+      {3, 300, 100, 33, true, true, true, true},        {2, 1000, 1000, 1, true, true, false, true},
+      {2, 516, 516, 8, false, true, false, false},      {1, 640, 640, 17, true, false, false, false},
+      {2, 384, 384, 32, true, true, false, false},      {1, 780, 780, 48, true, true, false, false},
+      {1, 520, 520, 64, true, true, false, false},      {2, 5000, 5000, 33, true, true, false, false},
+      {4, 5000, 100, 33, true, true, true, true},       {40, 300, 300, 33, true, true, false, false},
+  };
+  for (int bk : {16, 32}) {
+    for (int lo : {0, 1}) {
+      for (const Case& cs : cases) {
+        if (lo == 1 && !(cs.M == 700)) continue;  // the other conversion model on one shape only
+        double de;
+        int st;
+        lob::DsConfig cfg{bk, 0, 0, lo, 0, 0};
+        const double err = run_case(cs, cfg, 40, &de, &st);
+        const bool ok = (lo == 1) || (err < 2e-6 && de < 1e-12);
+        if (!ok) ++failures;
+        printf("[case] BK=%d lo=%d B=%lld M=%lld K=%lld C=%lld diag=%d dots=%d ex=%d : err %.3e dots_err %.3e %s\n", bk,
+               lo, (long long)cs.B, (long long)cs.M, (long long)cs.K, (long long)cs.C, cs.diag, cs.dots, cs.ex, err, de,
+               ok ? "ok" : "FAIL");
+        fflush(stdout);
+      }
+    }
+  }
+
+  }  // !perf_only
+  // ---------------- 3. throughput + repeatability at the config-2 shape ----------------
+  {
+    const int64_t B = perfB, N = perfN, C = 33;
+    float* A = dalloc_fill((size_t)B * N * N, 11);
+    float* X = dalloc_fill((size_t)B * N * C, 22);
+    float* d = dalloc_fill((size_t)B * N, 55);
+    float *Y, *Y0;
+    CK(cudaMalloc(&Y, (size_t)B * N * C * 4));
+    CK(cudaMalloc(&Y0, (size_t)B * N * C * 4));
+    const int n_parts = (int)((N + 127) / 128);
+    double* dots;
+    CK(cudaMalloc(&dots, (size_t)B * n_parts * C * 8));
+    const size_t wsb = lob::dense_stream_workspace_bytes(B, N, C);
+    void* ws;
+    CK(cudaMalloc(&ws, wsb));
+    CK(cudaDeviceSynchronize());
+    const double bytes = 4.0 * B * ((double)N * N + 2.0 * N * C);
+    struct V {
+      int bk, sa, sl, grid, dbg;
+    };
+    const V variants[] = {{16, 0, 3, 0, 0},       {32, 0, 2, 0, 0},      {16, 0, 2, 0, 0},        {16, 0, 4, 0, 0},
+                          {16, 0, 3, 0, 128},     {16, 0, 3, 0, 128 + 1}, {16, 0, 3, 0, 128 + 2},  {16, 0, 3, 0, 128 + 4},
+                          {16, 0, 3, 0, 128 + 6}, {16, 0, 3, 0, 128 + 14}, {32, 0, 2, 0, 128},     {32, 0, 2, 0, 128 + 1},
+                          {32, 0, 2, 0, 128 + 6}, {32, 0, 2, 0, 128 + 14}, {16, 4, 3, 0, 0},       {16, 6, 3, 0, 0}};
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    bool have_ref = false;
+    for (const V& v : variants) {
+      lob::DsConfig cfg{v.bk, v.sa, v.sl, 0, v.grid, v.dbg};
+      int s = lob::dense_matmul_stream_f32_cfg(B, N, N, C, A, N, N * N, X, Y, nullptr, nullptr, 0, d, N, 1, dots, ws,
+                                               wsb, 0, cfg);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (s != 0 || e != cudaSuccess) {
+        printf("[perf] BK=%d SA=%d SL=%d grid=%d: status %d (%s) cuda %s\n", v.bk, v.sa, v.sl, v.grid, s,
+               lob_last_error(), cudaGetErrorString(e));
+        if (e != cudaSuccess) return 3;
+        continue;
+      }
+      if (!have_ref) {
+        CK(cudaMemcpy(Y0, Y, (size_t)B * N * C * 4, cudaMemcpyDeviceToDevice));
+        have_ref = true;
+      }
+      float best = 1e30f, tot = 0.f;
+      for (int r = 0; r < reps; ++r) {
+        CK(cudaEventRecord(e0));
+        lob::dense_matmul_stream_f32_cfg(B, N, N, C, A, N, N * N, X, Y, nullptr, nullptr, 0, d, N, 1, dots, ws, wsb, 0,
+                                         cfg);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+        tot += ms;
+      }
+      // repeatability: the result must be bit-identical to the first variant's result (same arithmetic order)
+      std::vector<float> h((size_t)B * N * C), h0((size_t)B * N * C);
+      CK(cudaMemcpy(h.data(), Y, h.size() * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h0.data(), Y0, h0.size() * 4, cudaMemcpyDeviceToHost));
+      size_t diff = 0;
+      for (size_t i = 0; i < h.size(); ++i)
+        if (memcmp(&h[i], &h0[i], 4) != 0) ++diff;
+      if (diff && !v.dbg) ++failures;
+      printf("[perf] B=%lld N=%lld BK=%d SA=%d SL=%d grid=%d dbg=%d: best %.3f ms avg %.3f ms (split+matmul) -> %.1f GB/s "
+             "(best) | mismatches vs first variant: %zu\n",
+             (long long)B, (long long)N, v.bk, v.sa, v.sl, v.grid, v.dbg, best, tot / reps, bytes / best * 1e-6, diff);
+      fflush(stdout);
+    }
+    // spot check of the perf-shape result against the host
+    {
+      std::vector<float> h((size_t)B * N * C);
+      CK(cudaMemcpy(h.data(), Y0, h.size() * 4, cudaMemcpyDeviceToHost));
+      double worst = 0;
+      for (int i = 0; i < 48; ++i) {
+        const int64_t b = hash32(9000 + i) % B, r = hash32(9100 + i) % N;
+        for (int64_t c = 0; c < C; ++c) {
+          double acc = 0, accabs = 0;
+          for (int64_t k = 0; k < N; ++k) {
+            const double a = rnd(11, (uint64_t)((b * N + r) * N + k));
+            const double x = rnd(22, (uint64_t)((b * N + k) * C + c));
+            acc += a * x;
+            accabs += fabs(a * x);
+          }
+          const double dv = rnd(55, (uint64_t)(b * N + r));
+          const double ev = rnd(22, (uint64_t)((b * N + r) * C + c));
+          acc += dv * ev;
+          accabs += fabs(dv * ev);
+          worst = std::max(worst, fabs((double)h[(size_t)(b * N + r) * C + c] - acc) / accabs);
+        }
+      }
+      printf("[perf] spot check vs fp64 host: normalised err %.3e %s\n", worst, worst < 2e-6 ? "ok" : "FAIL");
+      if (!(worst < 2e-6)) ++failures;
+    }
+  }
+  printf("[harness] failures: %d\n", failures);
+  return failures ? 1 : 0;
+}

@@ -1,5 +1,7 @@
-"""The tcgen05 3xTF32 dense operator matmul (csrc/dense_tc.cu) against an fp64 product of the same fp32 inputs and
-against the CUDA-core kernel.  fp32 inputs; the bar is fp32 accuracy (error << 1e-4, north-star parity tolerance)."""
+"""The tcgen05 split-TF32 dense operator matmuls (csrc/dense_stream.cu: persistent streaming kernel, the default;
+csrc/dense_tc.cu: first-generation kernel, kept as the workspace-free fallback) against an fp64 product of the same fp32
+inputs and against the CUDA-core kernel.  fp32 inputs; the bar is fp32 accuracy (error << 1e-4, north-star parity
+tolerance)."""
 import os
 
 import pytest
@@ -10,6 +12,14 @@ pytestmark = pytest.mark.gpu
 from linear_operator_b200 import _kernels  # noqa: E402
 
 DEV = "cuda:0"
+
+
+@pytest.fixture(params=["stream", "tc"])
+def impl(request):
+    """Pins the fp32 tensor-core kernel through LOB_DENSE_IMPL (read by the library on every call)."""
+    os.environ["LOB_DENSE_IMPL"] = request.param
+    yield request.param
+    del os.environ["LOB_DENSE_IMPL"]
 
 
 def _case(B, N, C, with_diag, seed):
@@ -26,9 +36,9 @@ def _case(B, N, C, with_diag, seed):
 @pytest.mark.parametrize(
     "B,N,C,with_diag",
     [(2, 384, 33, True), (1, 260, 1, False), (2, 1000, 17, True), (2, 512, 48, True), (3, 2052, 33, True),
-     (1, 128, 8, False), (2, 5000, 33, True)],
+     (1, 128, 8, False), (2, 5000, 33, True), (2, 776, 64, True), (40, 300, 33, True)],
 )
-def test_dense_tc_matches_fp64(B, N, C, with_diag):
+def test_dense_tc_matches_fp64(B, N, C, with_diag, impl):
     A, X, d, ref = _case(B, N, C, with_diag, 100 + N + C)
     Y, dots, n_parts = _kernels.dense_matmul(A, X, d=d, want_dots=True)
     torch.cuda.synchronize()
@@ -53,7 +63,7 @@ def test_dense_tc_matches_fp64(B, N, C, with_diag):
     assert ((Y - Y2).abs().max() / scale).item() < 3e-6 + 3.5e-9 * N
 
 
-def test_dense_tc_plain_tf32_would_fail():
+def test_dense_tc_plain_tf32_would_fail(impl):
     """Sanity of the bar itself: a single-pass TF32 product is ~1e-3 off, the 3xTF32 kernel is not."""
     A, X, d, ref = _case(1, 1024, 33, False, 7)
     prev = torch.backends.cuda.matmul.allow_tf32
@@ -65,10 +75,10 @@ def test_dense_tc_plain_tf32_would_fail():
     e_tf32 = ((tf32.double() - ref).abs().max() / ref.abs().max()).item()
     Y = _kernels.dense_matmul(A, X)
     e_ours = ((Y.double() - ref).abs().max() / ref.abs().max()).item()
-    assert e_ours < 3e-6 and e_ours < e_tf32 / 20
+    assert e_ours < 3e-6 + 3.5e-9 * 1024 and e_ours < e_tf32 / 20
 
 
-def test_dense_tc_back_to_back_launches_are_deterministic():
+def test_dense_tc_back_to_back_launches_are_deterministic(impl):
     """Stress: 12 launches of a 960-CTA problem queued without host synchronisation must be bit-identical and agree
     with the CUDA-core kernel.  Regression test for a pipeline hazard found while speeding the kernel up: variants
     that issue tcgen05.mma within ~100 cycles of the tcgen05.st that produced their TMEM operand corrupt single rows
@@ -95,7 +105,7 @@ def test_dense_tc_back_to_back_launches_are_deterministic():
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("constant_diag", [True, False])
-def test_dense_matmul_generalised_epilogue(dtype, constant_diag):
+def test_dense_matmul_generalised_epilogue(dtype, constant_diag, impl):
     """Y = alpha[b] (A X) + d (.) E and the partial sums of E * Y -- the fused precondition_closure form
     (A = Q, X = Q^T r, E = r).  fp32 goes through the tensor-core kernel (K = 100), fp64 through the CUDA-core one."""
     B, N, k, C = 3, 1000, 100, 33
@@ -116,3 +126,21 @@ def test_dense_matmul_generalised_epilogue(dtype, constant_diag):
     T2 = _kernels.dense_matmul(Qt, E)
     ref2 = Qt.double() @ E.double()
     assert ((T2.double() - ref2).abs().max() / ref2.abs().max()).item() < tol
+
+
+def test_dense_stream_accumulation_bias_on_positive_data():
+    """Worst case for the tensor core's truncating fp32 accumulate: all-positive operands, no cancellation.  The bias is
+    linear in K (measured 1.5e-8 * K relative); this pins it below the 1e-4 parity bar at N = 5000 and documents it."""
+    os.environ["LOB_DENSE_IMPL"] = "stream"
+    try:
+        g = torch.Generator(device=DEV).manual_seed(11)
+        A = torch.rand(1, 512, 5000, device=DEV, generator=g)
+        X = torch.rand(1, 5000, 16, device=DEV, generator=g)
+        Y = _kernels.dense_matmul(A, X)
+    finally:
+        del os.environ["LOB_DENSE_IMPL"]
+    ref = A.double() @ X.double()
+    rel = ((Y.double() - ref).abs() / ref.abs()).max().item()
+    print(f"all-positive K=5000: rel err {rel:.3e}")
+    assert rel < 1e-4
+    assert (Y.double() <= ref * (1 + 1e-6)).all()  # truncation only ever loses magnitude

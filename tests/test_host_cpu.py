@@ -47,7 +47,7 @@ def test_argument_errors_come_back_through_the_abi():
     lib = _lib.load()
     p = _lib.CgParams(0, 10, 1, 0, 0, 0, 10, 10, 0, 1.0, 1e-10, 1e-10)
     assert lib.lob_cg_workspace_bytes(ctypes.byref(p)) == 0
-    rc = lib.lob_dense_matmul(0, 0, 4, 4, 1, None, 4, 16, None, None, None, 0, 0, None, None)
+    rc = lib.lob_dense_matmul(0, 0, 4, 4, 1, None, 4, 16, None, None, None, 0, 0, None, None, 0, None)
     assert rc == -1 and b"positive" in lib.lob_last_error()
     rc = lib.lob_tn_matmul(7, 0, 1, 4, 2, 2, None, 0, None, 0, None, None, None)
     assert rc == -1
