@@ -13,7 +13,7 @@ objs=()
 for src in "$HERE"/*.cu; do
   o="$OBJ/$(basename "${src%.cu}").o"
   objs+=("$o")
-  if [[ ! -f "$o" || "$src" -nt "$o" || "$HERE/common.cuh" -nt "$o" || "$HERE/simt_tile.cuh" -nt "$o" || "$ROOT/include/lob_b200.h" -nt "$o" ]]; then
+  if [[ ! -f "$o" || "$src" -nt "$o" || "$HERE/common.cuh" -nt "$o" || "$HERE/simt_tile.cuh" -nt "$o" || "$HERE/tcgen05_util.cuh" -nt "$o" || "$ROOT/include/lob_b200.h" -nt "$o" ]]; then
     "$NVCC" "${FLAGS[@]}" ${LOB_PTXAS_V:+-Xptxas -v} -c "$src" -o "$o" &
     pids+=($!)
   fi

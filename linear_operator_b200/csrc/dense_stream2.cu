@@ -1,0 +1,466 @@
+// dense_stream2.cu -- second-generation streaming kernel for the fp32 dense operator matmul  Y = alpha (A X) + d (.) E.
+// Reference arithmetic: operators/dense_linear_operator.py:60-64, operators/added_diag_linear_operator.py:72-76,135-140,
+// utils/linear_cg.py:250-251 (fused <p, Ap>).
+//
+// Same persistent skeleton as dense_stream.cu (one CTA per SM, static tile schedule, TMA ring, elect.sync'd UMMA issue,
+// double-buffered TMEM accumulators drained by dedicated epilogue warps), but "A-stationary": ncu showed the first
+// kernel saturating the shared-memory data pipe (tensor-core operand reads 36 % + converter LDS/STS 39 % + TMA writes
+// 16 % at 0.63 of the HBM roofline), so this one moves less through shared memory:
+//   * the operator tile (256 rows x BK columns, as TMA lands it) is the UMMA *A* operand of two M = 128 MMAs per k step,
+//     read raw from shared memory (the tensor core drops the 13 low mantissa bits: A_hi for free);
+//   * A_lo = A - tf32(A) never goes back to shared memory: each converter thread owns one operator row, reads its BK
+//     values (swizzle-aware, conflict-free LDS.128), and stores the correction straight into a TMEM operand slot
+//     (tcgen05.st); a second, narrower MMA per k step takes its A operand from TMEM;
+//   * the right-hand side is the UMMA *B* operand, N = 2 CP rows [X_hi ; X_lo] (CP = C rounded up to 8), K-major,
+//     pre-split into a workspace by k_split_x2 and TMA-loaded beside the A tile.  Only 2 CP x BK x 4 bytes of it are
+//     read per MMA (vs. 8 KB of A_lo + 4 KB of X in the first kernel), and the tensor time per k step drops from
+//     2 x 128 to 2 x (CP/2.67 + CP/5.3) cycles.
+//   D[:, c] = A_hi X_hi + A_lo X_hi,  D[:, CP + c] = A_hi X_lo:  y = D[:, c] + D[:, CP + c]   (3xTF32, fp32 accumulate)
+// TMEM (512 columns): 4 accumulators x 96 columns (2 M tiles x 2 buffers) + 128 columns of A_lo operand slots.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tcgen05_util.cuh"
+
+namespace lob {
+
+constexpr int D2_ROWS = 256;  // operator rows per tile (two UMMA M = 128 tiles)
+constexpr int D2_THREADS = 512;
+constexpr int D2_ACC_COLS = 96;
+constexpr int D2_SLOT_BASE = 4 * D2_ACC_COLS;  // 384
+constexpr int D2_MAX_ST = 12;
+constexpr int D2_RED_DOUBLES = 2 * 2 * 4 * 48;  // [buffer][tile][quarter][column]
+
+struct D2Params {
+  float* Y;
+  const float* E;
+  const float* alpha;
+  int64_t alpha_bs;
+  const float* dg;
+  int64_t d_bs, d_st;
+  double* dots;
+  int64_t M, K, C;
+  int n_parts;
+  int CP;        // C rounded up to 8: X_hi rows [0, CP), X_lo rows [CP, 2 CP)
+  int xbytes;    // bytes of one X tile (2 CP x BK x 4, rounded up to 1 KB)
+  int SA;        // ring stages
+  int MT;
+  int64_t ntiles;
+  int a_shared;
+  uint32_t idesc_hi, idesc_lo;
+  int dbg;       // harness experiments: 1 skip lo MMA, 2 skip conversion, 4 skip all MMAs
+};
+
+template <int BK>
+__global__ void __launch_bounds__(D2_THREADS, 1)
+k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX, D2Params p) {
+  using namespace ds;
+  constexpr int A_STAGE = D2_ROWS * BK * 4;
+  constexpr int NSLOT = 128 / (2 * BK);  // A_lo operand slots in TMEM (each: 2 M tiles x BK columns)
+  constexpr int ROW_BYTES = BK * 4;
+  constexpr int NU = BK / 4;  // 16-byte units per operator row
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stage_bytes = A_STAGE + p.xbytes;
+  unsigned char* sRing = smem;
+  double* dred = reinterpret_cast<double*>(smem + p.SA * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dred + D2_RED_DOUBLES);
+  uint64_t* full = bars;                    // [MAX_ST] TMA -> converters, MMA
+  uint64_t* empty = full + D2_MAX_ST;       // [MAX_ST] MMA (commit) -> TMA
+  uint64_t* lo_full = empty + D2_MAX_ST;    // [NSLOT]  converters -> MMA
+  uint64_t* lo_empty = lo_full + 4;         // [NSLOT]  MMA (commit) -> converters
+  uint64_t* acc_full = lo_empty + 4;        // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (int)((p.K + BK - 1) / BK);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    for (int i = 0; i < p.SA; ++i) {
+      mbar_init(smem_u32(&full[i]), 1);
+      mbar_init(smem_u32(&empty[i]), 1);
+    }
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(smem_u32(&lo_full[i]), 8);
+      mbar_init(smem_u32(&lo_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&acc_full[i]), 1);
+      mbar_init(smem_u32(&acc_empty[i]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_holder))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint64_t pol_stream, pol_keep;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t xtx = (uint32_t)(2 * p.CP * BK * 4);
+      for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int b = (int)(tile / p.MT);
+        const int m0 = (int)(tile - (int64_t)b * p.MT) * D2_ROWS;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+          const uint32_t dst = smem_u32(sRing + s * stage_bytes);
+          const uint32_t bar = smem_u32(&full[s]);
+          mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE + xtx);
+          tma_load_3d(dst + A_STAGE, &tmX, bar, kb * BK, 0, b, pol_keep);
+          tma_load_3d(dst, &tmA, bar, kb * BK, m0, p.a_shared ? 0 : b, pol_stream);
+          if (++s == p.SA) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int s = 0, sl = 0;
+    uint32_t ph = 0, phl = 0, it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      mbar_wait(smem_u32(&acc_empty[buf]), ((it >> 1) & 1) ^ 1);
+      const uint32_t d0 = tmem_base + buf * 2 * D2_ACC_COLS;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(smem_u32(&full[s]), ph);
+        mbar_wait(smem_u32(&lo_full[sl]), phl);
+        __syncwarp();
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(sRing + s * stage_bytes);
+          const uint64_t xdesc = make_kmajor_desc<BK>(a_addr + A_STAGE);
+          const uint32_t lo_slot = tmem_base + D2_SLOT_BASE + sl * (2 * BK);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const uint64_t adesc = make_kmajor_desc<BK>(a_addr + t * (128 * ROW_BYTES));
+            const uint32_t d_addr = d0 + t * D2_ACC_COLS;
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 8 tf32 = 32 bytes inside the swizzle span
+              if (!(p.dbg & 4)) umma_tf32_ss(d_addr, adesc + adv, xdesc + adv, p.idesc_hi, (kb | k) ? 1u : 0u);
+              if (!(p.dbg & 5)) umma_tf32_ts(d_addr, lo_slot + t * BK + k * 8, xdesc + adv, p.idesc_lo, 1u);
+            }
+          }
+          umma_commit(smem_u32(&empty[s]));
+          umma_commit(smem_u32(&lo_empty[sl]));
+          if (kb == nkb - 1) umma_commit(smem_u32(&acc_full[buf]));
+        }
+        __syncwarp();
+        if (++s == p.SA) { s = 0; ph ^= 1; }
+        if (++sl == NSLOT) { sl = 0; phl ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue: thread = operator row =====================
+    const int q = warp & 3;
+    const int C = (int)p.C, CP = p.CP;
+    const bool need_e = (p.dg != nullptr) || (p.dots != nullptr);
+    const int et = threadIdx.x - 128;  // 0..127 inside the epilogue group
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      const int64_t b = tile / p.MT;
+      const int mt = (int)(tile - b * p.MT);
+      const int64_t m0 = (int64_t)mt * D2_ROWS;
+      const float alpha_b = p.alpha ? p.alpha[b * p.alpha_bs] : 1.0f;
+      const float* Eb = p.E + b * p.M * C;
+      float* Yb = p.Y + b * p.M * C;
+      double* red = dred + buf * (2 * 4 * 48);
+      mbar_wait(smem_u32(&acc_full[buf]), (it >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int64_t row = m0 + t * 128 + q * 32 + lane;
+        const bool rok = row < p.M;
+        const float dv = (p.dg && rok) ? __ldg(p.dg + b * p.d_bs + row * p.d_st) : 0.f;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + t) * D2_ACC_COLS;
+#pragma unroll 1
+        for (int c0 = 0; c0 < CP; c0 += 16) {
+          float e[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) e[i] = (need_e && rok && c0 + i < C) ? __ldg(Eb + row * C + c0 + i) : 0.f;
+          uint32_t hi[16], lo[16];
+          DS_LD16(taddr + c0, hi);
+          DS_LD16(taddr + CP + c0, lo);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float y = fmaf(dv, e[i], (__uint_as_float(hi[i]) + __uint_as_float(lo[i])) * alpha_b);
+            if (rok && c0 + i < C) Yb[row * C + c0 + i] = y;
+            if (p.dots) {
+              // column sum of e * y over the 32 rows of this warp (fixed butterfly order: deterministic)
+              double pd = (rok && c0 + i < C) ? (double)e[i] * (double)y : 0.0;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) pd += __shfl_xor_sync(0xffffffffu, pd, o);
+              if (lane == i) red[(t * 4 + q) * 48 + c0 + i] = pd;
+            }
+          }
+        }
+      }
+      // accumulators drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+      if (p.dots) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int idx = et; idx < 2 * C; idx += 128) {
+          const int t = idx / C, c = idx - t * C;
+          const int64_t pi = (int64_t)mt * 2 + t;
+          if (pi < p.n_parts) {
+            const double* r4 = red + t * 4 * 48 + c;
+            p.dots[(b * p.n_parts + pi) * C + c] = (r4[0] + r4[48]) + (r4[96] + r4[144]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== converters: A_lo rows -> TMEM operand slot =====================
+    const int q = warp & 3;
+    const int t = (warp - 8) >> 2;
+    const int row = t * 128 + q * 32 + lane;
+    const uint32_t swz = (BK == 32) ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + D2_SLOT_BASE + t * BK;
+    int s = 0, sl = 0;
+    uint32_t ph = 0, phl = 0;
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(smem_u32(&full[s]), ph);
+        const unsigned char* arow = sRing + s * stage_bytes + row * ROW_BYTES;
+        uint32_t lo[BK];
+        if (!(p.dbg & 2)) {
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            const uint4 v = *reinterpret_cast<const uint4*>(arow + ((u ^ swz) << 4));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float l = __uint_as_float(w[j]) - __uint_as_float(w[j] & 0xFFFFE000u);
+              lo[u * 4 + j] = (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;  // tf32, round to nearest
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < BK; ++j) lo[j] = 0u;
+        }
+        mbar_wait(smem_u32(&lo_empty[sl]), phl ^ 1);
+        __syncwarp();
+        tc_fence_after();
+        const uint32_t taddr = lane_addr + sl * (2 * BK);
+        DS_ST16(taddr, lo);
+        if constexpr (BK == 32) DS_ST16(taddr + 16, (lo + 16));
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&lo_full[sl]));
+        if (++s == p.SA) { s = 0; ph ^= 1; }
+        if (++sl == NSLOT) { sl = 0; phl ^= 1; }
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Xs (B, 2 CP, Kp): rows [0, CP) = tf32(x[:, c]), rows [CP, 2 CP) = tf32(x - hi); k >= K and c >= C are zeros.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SPLIT2_KT = 64;
+
+__global__ void __launch_bounds__(256)
+k_split_x2(const float* __restrict__ X, float* __restrict__ Xs, int64_t K, int64_t Kp, int C, int CP) {
+  extern __shared__ float xs2[];  // [SPLIT2_KT][C | 1]
+  const int ldx = C | 1;
+  const int64_t b = blockIdx.y;
+  const int64_t k0 = (int64_t)blockIdx.x * SPLIT2_KT;
+  const int kvalid = (int)max((int64_t)0, min((int64_t)SPLIT2_KT, K - k0));
+  const float* src = X + (b * K + k0) * C;
+  for (int e = threadIdx.x; e < kvalid * C; e += blockDim.x) xs2[(e / C) * ldx + (e % C)] = src[e];
+  __syncthreads();
+  const int kk = threadIdx.x & (SPLIT2_KT - 1);
+  const int kw = (int)min((int64_t)SPLIT2_KT, Kp - k0);
+  const int R = 2 * CP;
+  for (int r = threadIdx.x / SPLIT2_KT; r < R; r += blockDim.x / SPLIT2_KT) {
+    const int part = r >= CP;
+    const int c = r - part * CP;
+    float out = 0.f;
+    if (c < C && kk < kvalid) {
+      const float x = xs2[kk * ldx + c];
+      const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+      out = part == 0 ? hi : __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
+    }
+    if (kk < kw) Xs[(b * R + r) * Kp + k0 + kk] = out;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled_d2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled_d2 d2_encode_fn() {
+  static PFN_encodeTiled_d2 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled_d2)ptr;
+  }
+  return fn;
+}
+
+struct D2Config {
+  int bk;    // 16 (SWIZZLE_64B) or 32 (SWIZZLE_128B)
+  int sa;    // ring depth (0 = deepest that fits)
+  int grid;  // 0 = one CTA per SM
+  int dbg;
+};
+
+static D2Config d2_default_config() {
+  static D2Config cfg = [] {
+    D2Config c{32, 0, 0, 0};
+    if (const char* e = getenv("LOB_D2_BK")) c.bk = atoi(e);
+    if (const char* e = getenv("LOB_D2_SA")) c.sa = atoi(e);
+    if (const char* e = getenv("LOB_D2_GRID")) c.grid = atoi(e);
+    return c;
+  }();
+  return cfg;
+}
+
+constexpr size_t D2_SMEM_MAX = 232448;
+constexpr size_t D2_SMEM_FIXED = 1024 /*alignment*/ + D2_RED_DOUBLES * 8 + 512 /*barriers*/;
+
+size_t dense_stream2_workspace_bytes(int64_t B, int64_t K, int64_t C) {
+  if (B <= 0 || K <= 0 || C <= 0 || C > 48) return 0;
+  const int64_t CP = (C + 7) / 8 * 8;
+  const int64_t Kp = (K + 3) / 4 * 4;
+  return (size_t)B * 2 * CP * Kp * sizeof(float);
+}
+
+// returns LOB_ERR_UNSUPPORTED when the shape does not qualify (caller falls back to another CUDA kernel)
+int dense_matmul_stream2_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
+                                 const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
+                                 const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
+                                 cudaStream_t st, D2Config cfg) {
+  if (C > 48 || C < 1) return LOB_ERR_UNSUPPORTED;
+  if ((lda % 4) != 0 || (a_bs % 4) != 0 || (reinterpret_cast<uintptr_t>(A) & 15) != 0) return LOB_ERR_UNSUPPORTED;
+  if (M >= (1LL << 31) || K >= (1LL << 31) || B >= (1LL << 31)) return LOB_ERR_UNSUPPORTED;
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15) != 0 || ws_bytes < dense_stream2_workspace_bytes(B, K, C))
+    return LOB_ERR_UNSUPPORTED;
+  if ((d || dots) && !E && M != K) return LOB_ERR_UNSUPPORTED;
+  PFN_encodeTiled_d2 enc = d2_encode_fn();
+  if (!enc) return LOB_ERR_UNSUPPORTED;
+  const int BK = (cfg.bk == 32) ? 32 : 16;
+  const int CP = (int)((C + 7) / 8 * 8);
+  const int64_t Kp = (K + 3) / 4 * 4;
+  const bool shared = (a_bs == 0);
+  const CUtensorMapSwizzle swz = (BK == 32) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+
+  CUtensorMap tmA, tmX;
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)M, (cuuint64_t)(shared ? 1 : B)};
+    cuuint64_t gstr[2] = {(cuuint64_t)lda * 4, (cuuint64_t)(shared ? (cuuint64_t)M * lda : a_bs) * 4};
+    cuuint32_t box[3] = {(cuuint32_t)BK, D2_ROWS, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(A), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return LOB_ERR_UNSUPPORTED;
+  }
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)(2 * CP), (cuuint64_t)B};
+    cuuint64_t gstr[2] = {(cuuint64_t)Kp * 4, (cuuint64_t)(2 * CP) * Kp * 4};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(2 * CP), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ws, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return LOB_ERR_UNSUPPORTED;
+  }
+
+  if (!(cfg.dbg & 128)) {
+    dim3 grid((unsigned)cdiv(Kp, SPLIT2_KT), (unsigned)B);
+    const size_t sm = (size_t)SPLIT2_KT * ((int)C | 1) * sizeof(float);
+    k_split_x2<<<grid, 256, sm, st>>>(X, (float*)ws, K, Kp, (int)C, CP);
+    LOB_TRY(check_launch("k_split_x2"));
+  }
+
+  const int a_stage = D2_ROWS * BK * 4;
+  const int xbytes = (int)align_up((size_t)2 * CP * BK * 4, 1024);
+  const int stage = a_stage + xbytes;
+  int sa = cfg.sa > 0 ? cfg.sa : (int)((D2_SMEM_MAX - D2_SMEM_FIXED) / stage);
+  if (sa > D2_MAX_ST) sa = D2_MAX_ST;
+  if (sa < 2) return LOB_ERR_UNSUPPORTED;
+  const size_t smem = D2_SMEM_FIXED + (size_t)sa * stage;
+  if (smem > D2_SMEM_MAX) return LOB_ERR_UNSUPPORTED;
+
+  D2Params p;
+  p.Y = Y;
+  p.E = E ? E : X;
+  p.alpha = alpha;
+  p.alpha_bs = alpha_bs;
+  p.dg = d;
+  p.d_bs = d_bs;
+  p.d_st = d_st;
+  p.dots = dots;
+  p.M = M;
+  p.K = K;
+  p.C = C;
+  p.n_parts = (int)cdiv(M, 128);
+  p.CP = CP;
+  p.xbytes = xbytes;
+  p.SA = sa;
+  p.MT = (int)cdiv(M, D2_ROWS);
+  p.ntiles = B * p.MT;
+  p.a_shared = shared ? 1 : 0;
+  p.idesc_hi = ds::make_idesc_tf32(128, 2 * CP);
+  // UMMA M = 128 needs N % 16 == 0: when CP is an odd multiple of 8 the narrow MMA also covers the first 8 X_lo rows,
+  // which only adds the (otherwise dropped, O(2^-22)) a_lo * x_lo terms of those columns
+  p.idesc_lo = ds::make_idesc_tf32(128, (CP + 15) / 16 * 16);
+  p.dbg = cfg.dbg;
+  const int64_t grid = std::min<int64_t>(p.ntiles, cfg.grid > 0 ? cfg.grid : kNumSMs);
+  if (BK == 32) {
+    auto kern = k_dense_stream2<32>;
+    LOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D2_SMEM_MAX));
+    kern<<<(unsigned)grid, D2_THREADS, smem, st>>>(tmA, tmX, p);
+  } else {
+    auto kern = k_dense_stream2<16>;
+    LOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D2_SMEM_MAX));
+    kern<<<(unsigned)grid, D2_THREADS, smem, st>>>(tmA, tmX, p);
+  }
+  return check_launch("k_dense_stream2");
+}
+
+int dense_matmul_stream2_f32(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
+                             const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
+                             const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
+                             cudaStream_t st) {
+  return dense_matmul_stream2_f32_cfg(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, ws,
+                                      ws_bytes, st, d2_default_config());
+}
+
+}  // namespace lob

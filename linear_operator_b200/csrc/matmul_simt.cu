@@ -283,8 +283,15 @@ int dense_matmul_stream_f32(int64_t B, int64_t M, int64_t K, int64_t C, const fl
                             const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
                             cudaStream_t st);
 
-// fp32 dispatch: streaming tcgen05 kernel (needs the workspace) -> first-generation tcgen05 kernel -> CUDA cores.
-// LOB_DENSE_IMPL = stream | tc | simt pins one of them (diagnostics, A/B comparisons).
+size_t dense_stream2_workspace_bytes(int64_t B, int64_t K, int64_t C);
+int dense_matmul_stream2_f32(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
+                             const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
+                             const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
+                             cudaStream_t st);
+
+// fp32 dispatch: streaming tcgen05 kernels (need the workspace; dense_stream2.cu for C <= 48, dense_stream.cu up to
+// C = 64) -> first-generation tcgen05 kernel -> CUDA cores.
+// LOB_DENSE_IMPL = stream2 | stream | tc | simt pins one of them (diagnostics, A/B comparisons).
 static int dense_f32_tensor_paths(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
                                   const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
                                   const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
@@ -293,6 +300,12 @@ static int dense_f32_tensor_paths(int64_t B, int64_t M, int64_t K, int64_t C, co
   if (getenv("LOB_DISABLE_TC") || (impl && !strcmp(impl, "simt"))) return LOB_ERR_UNSUPPORTED;
   // Short contractions (the K = rank preconditioner product Q t) are per-tile-overhead bound in the persistent kernel
   // (few k-blocks per 256-row tile, epilogue not hidden): they stay on the first-generation kernel unless pinned.
+  const bool pinned_stream2 = impl && !strcmp(impl, "stream2");
+  if (pinned_stream2 || (!impl && K >= 512)) {
+    int s = dense_matmul_stream2_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, ws,
+                                     ws_bytes, st);
+    if (s != LOB_ERR_UNSUPPORTED) return s;
+  }
   const bool pinned_stream = impl && !strcmp(impl, "stream");
   if (pinned_stream || (!impl && K >= 512)) {
     int s = dense_matmul_stream_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, ws,
@@ -306,7 +319,8 @@ static int dense_f32_tensor_paths(int64_t B, int64_t M, int64_t K, int64_t C, co
 extern "C" size_t lob_dense_matmul_workspace_bytes(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C) {
   (void)M;
   if (dtype != LOB_F32) return 0;
-  return lob::dense_stream_workspace_bytes(B, K, C);
+  const size_t w1 = lob::dense_stream_workspace_bytes(B, K, C), w2 = lob::dense_stream2_workspace_bytes(B, K, C);
+  return w1 > w2 ? w1 : w2;
 }
 
 extern "C" int lob_dense_matmul_ex(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A,

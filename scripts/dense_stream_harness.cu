@@ -25,7 +25,31 @@ int dense_matmul_stream_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, cons
                                 const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
                                 const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
                                 cudaStream_t st, DsConfig cfg);
+struct D2Config {
+  int bk, sa, grid, dbg;
+};
+size_t dense_stream2_workspace_bytes(int64_t B, int64_t K, int64_t C);
+int dense_matmul_stream2_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
+                                 const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
+                                 const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
+                                 cudaStream_t st, D2Config cfg);
 }  // namespace lob
+
+static int g_impl = 1;  // 1: dense_stream.cu, 2: dense_stream2.cu
+static size_t ws_bytes_for(int64_t B, int64_t K, int64_t C) {
+  return g_impl == 2 ? lob::dense_stream2_workspace_bytes(B, K, C) : lob::dense_stream_workspace_bytes(B, K, C);
+}
+static int launch(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs, const float* X,
+                  float* Y, const float* E, const float* alpha, int64_t alpha_bs, const float* d, int64_t d_bs,
+                  int64_t d_st, double* dots, void* ws, size_t wsb, lob::DsConfig cfg) {
+  if (g_impl == 2) {
+    lob::D2Config c2{cfg.bk, cfg.sa, cfg.grid, cfg.dbg};
+    return lob::dense_matmul_stream2_f32_cfg(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots,
+                                             ws, wsb, 0, c2);
+  }
+  return lob::dense_matmul_stream_f32_cfg(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, ws,
+                                          wsb, 0, cfg);
+}
 
 #define CK(x)                                                                        \
   do {                                                                               \
@@ -107,11 +131,10 @@ static double run_case(const Case& cs, lob::DsConfig cfg, int nsample_rows, doub
     CK(cudaMalloc(&dots, (size_t)B * n_parts * C * 8));
     CK(cudaMemset(dots, 0xFF, (size_t)B * n_parts * C * 8));
   }
-  const size_t wsb = lob::dense_stream_workspace_bytes(B, K, C);
+  const size_t wsb = ws_bytes_for(B, K, C);
   void* ws;
   CK(cudaMalloc(&ws, wsb));
-  int s = lob::dense_matmul_stream_f32_cfg(B, M, K, C, A, K, M * K, X, Y, E, al, 1, d, dn, cs.const_diag ? 0 : 1, dots,
-                                           ws, wsb, 0, cfg);
+  int s = launch(B, M, K, C, A, K, M * K, X, Y, E, al, 1, d, dn, cs.const_diag ? 0 : 1, dots, ws, wsb, cfg);
   *status = s;
   cudaError_t e = cudaDeviceSynchronize();
   if (s != 0 || e != cudaSuccess) {
@@ -224,11 +247,14 @@ int main(int argc, char** argv) {
   int perfN = argc > 2 ? atoi(argv[2]) : 5000;
   int reps = argc > 3 ? atoi(argv[3]) : 5;
   const bool perf_only = argc > 4 && strcmp(argv[4], "perfonly") == 0;
+  g_impl = argc > 5 ? atoi(argv[5]) : 1;
+  printf("[harness] kernel generation %d\n", g_impl);
   int failures = 0;
   if (!perf_only) {
 
   // ---------------- 1. fp32 -> tf32 conversion model of the tensor core ----------------
   for (int bk : {16, 32}) {
+    if (g_impl == 2) break;
     Case cs{1, 256, 512, 16, false, false, false, false};
     double de, me[2];
     int st;
@@ -260,7 +286,8 @@ int main(int argc, char** argv) {
   for (int bk : {16, 32}) {
     for (int lo : {0, 1}) {
       for (const Case& cs : cases) {
-        if (lo == 1 && !(cs.M == 700)) continue;  // the other conversion model on one shape only
+        if (lo == 1 && (g_impl == 2 || !(cs.M == 700))) continue;  // the other conversion model on one shape only
+        if (g_impl == 2 && cs.C > 48) continue;
         double de;
         int st;
         lob::DsConfig cfg{bk, 0, 0, lo, 0, 0};
@@ -288,7 +315,7 @@ int main(int argc, char** argv) {
     const int n_parts = (int)((N + 127) / 128);
     double* dots;
     CK(cudaMalloc(&dots, (size_t)B * n_parts * C * 8));
-    const size_t wsb = lob::dense_stream_workspace_bytes(B, N, C);
+    const size_t wsb = ws_bytes_for(B, N, C);
     void* ws;
     CK(cudaMalloc(&ws, wsb));
     CK(cudaDeviceSynchronize());
@@ -296,18 +323,20 @@ int main(int argc, char** argv) {
     struct V {
       int bk, sa, sl, grid, dbg;
     };
-    const V variants[] = {{16, 0, 3, 0, 0},       {32, 0, 2, 0, 0},      {16, 0, 2, 0, 0},        {16, 0, 4, 0, 0},
-                          {16, 0, 3, 0, 128},     {16, 0, 3, 0, 128 + 1}, {16, 0, 3, 0, 128 + 2},  {16, 0, 3, 0, 128 + 4},
-                          {16, 0, 3, 0, 128 + 6}, {16, 0, 3, 0, 128 + 14}, {32, 0, 2, 0, 128},     {32, 0, 2, 0, 128 + 1},
-                          {32, 0, 2, 0, 128 + 6}, {32, 0, 2, 0, 128 + 14}, {16, 4, 3, 0, 0},       {16, 6, 3, 0, 0}};
+    const V variants1[] = {{16, 0, 3, 0, 0}, {32, 0, 2, 0, 0}};
+    const V variants2[] = {{16, 0, 0, 0, 0},       {32, 0, 0, 0, 0},      {16, 4, 0, 0, 0},        {16, 6, 0, 0, 0},
+                           {16, 0, 0, 0, 128},     {16, 0, 0, 0, 128 + 1}, {16, 0, 0, 0, 128 + 2},  {16, 0, 0, 0, 128 + 4},
+                           {16, 0, 0, 0, 128 + 6}, {32, 0, 0, 0, 128 + 1}, {32, 0, 0, 0, 128 + 6}};
+    std::vector<V> variants;
+    if (g_impl == 2) variants.assign(variants2, variants2 + sizeof(variants2) / sizeof(V));
+    else variants.assign(variants1, variants1 + sizeof(variants1) / sizeof(V));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     bool have_ref = false;
     for (const V& v : variants) {
       lob::DsConfig cfg{v.bk, v.sa, v.sl, 0, v.grid, v.dbg};
-      int s = lob::dense_matmul_stream_f32_cfg(B, N, N, C, A, N, N * N, X, Y, nullptr, nullptr, 0, d, N, 1, dots, ws,
-                                               wsb, 0, cfg);
+      int s = launch(B, N, N, C, A, N, N * N, X, Y, nullptr, nullptr, 0, d, N, 1, dots, ws, wsb, cfg);
       cudaError_t e = cudaDeviceSynchronize();
       if (s != 0 || e != cudaSuccess) {
         printf("[perf] BK=%d SA=%d SL=%d grid=%d: status %d (%s) cuda %s\n", v.bk, v.sa, v.sl, v.grid, s,
@@ -322,8 +351,7 @@ int main(int argc, char** argv) {
       float best = 1e30f, tot = 0.f;
       for (int r = 0; r < reps; ++r) {
         CK(cudaEventRecord(e0));
-        lob::dense_matmul_stream_f32_cfg(B, N, N, C, A, N, N * N, X, Y, nullptr, nullptr, 0, d, N, 1, dots, ws, wsb, 0,
-                                         cfg);
+        launch(B, N, N, C, A, N, N * N, X, Y, nullptr, nullptr, 0, d, N, 1, dots, ws, wsb, cfg);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms;
