@@ -34,6 +34,7 @@ constexpr int D2_RED_DOUBLES = 2 * 2 * 4 * 48;  // [buffer][tile][quarter][colum
 
 struct D2Params {
   float* Y;
+  const float* X;      // (B, K, C) right-hand side (read by the in-kernel X producers when xmode == 1)
   const float* E;
   const float* alpha;
   int64_t alpha_bs;
@@ -49,6 +50,7 @@ struct D2Params {
   int64_t ntiles;
   int a_shared;
   uint32_t idesc_hi, idesc_lo;
+  int xmode;     // 0: X operand tiles TMA-loaded from the pre-split workspace; 1: produced in the kernel (warps 2-3)
   int dbg;       // harness experiments: 1 skip lo MMA, 2 skip conversion, 4 skip all MMAs
 };
 
@@ -69,7 +71,8 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(dred + D2_RED_DOUBLES);
   uint64_t* full = bars;                    // [MAX_ST] TMA -> converters, MMA
   uint64_t* empty = full + D2_MAX_ST;       // [MAX_ST] MMA (commit) -> TMA
-  uint64_t* lo_full = empty + D2_MAX_ST;    // [NSLOT]  converters -> MMA
+  uint64_t* x_full = empty + D2_MAX_ST;     // [MAX_ST] X producers -> MMA (xmode 1)
+  uint64_t* lo_full = x_full + D2_MAX_ST;   // [NSLOT]  converters -> MMA
   uint64_t* lo_empty = lo_full + 4;         // [NSLOT]  MMA (commit) -> converters
   uint64_t* acc_full = lo_empty + 4;        // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
@@ -84,6 +87,7 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int i = 0; i < p.SA; ++i) {
       mbar_init(smem_u32(&full[i]), 1);
       mbar_init(smem_u32(&empty[i]), 1);
+      mbar_init(smem_u32(&x_full[i]), 2);
     }
     for (int i = 0; i < NSLOT; ++i) {
       mbar_init(smem_u32(&lo_full[i]), 8);
@@ -100,6 +104,14 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (p.xmode == 1) {
+    // X tiles are written by the producer warps; their padding rows (c >= C) stay zero for the whole kernel
+    for (int s = 0; s < p.SA; ++s) {
+      uint4* xt = reinterpret_cast<uint4*>(smem + s * (A_STAGE + p.xbytes) + A_STAGE);
+      for (int i = threadIdx.x; i < p.xbytes / 16; i += D2_THREADS) xt[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -111,6 +123,10 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint64_t pol_stream, pol_keep;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      // measured (ncu dram__bytes_read): evict_first on the operator stream makes L2 drop the promoted 256-byte lines
+      // before the next k-block of the same rows needs their other half: +8.7 % DRAM reads.  evict_normal avoids it.
+      if (!(p.dbg & 512)) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_stream));
+      if (p.dbg & 256) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_stream));
       int s = 0;
       uint32_t ph = 0;
       const uint32_t xtx = (uint32_t)(2 * p.CP * BK * 4);
@@ -121,8 +137,12 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(smem_u32(&empty[s]), ph ^ 1);
           const uint32_t dst = smem_u32(sRing + s * stage_bytes);
           const uint32_t bar = smem_u32(&full[s]);
-          mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE + xtx);
-          tma_load_3d(dst + A_STAGE, &tmX, bar, kb * BK, 0, b, pol_keep);
+          if (p.xmode == 1) {
+            mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE);
+          } else {
+            mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE + xtx);
+            tma_load_3d(dst + A_STAGE, &tmX, bar, kb * BK, 0, b, pol_keep);
+          }
           tma_load_3d(dst, &tmA, bar, kb * BK, m0, p.a_shared ? 0 : b, pol_stream);
           if (++s == p.SA) { s = 0; ph ^= 1; }
         }
@@ -138,6 +158,7 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t d0 = tmem_base + buf * 2 * D2_ACC_COLS;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(smem_u32(&full[s]), ph);
+        if (p.xmode == 1) mbar_wait(smem_u32(&x_full[s]), ph);
         mbar_wait(smem_u32(&lo_full[sl]), phl);
         __syncwarp();
         tc_fence_after();
@@ -163,6 +184,84 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         if (++s == p.SA) { s = 0; ph ^= 1; }
         if (++sl == NSLOT) { sl = 0; phl ^= 1; }
+      }
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ===================== X producers (xmode 1): [X_hi ; X_lo] tile, K-major, hardware swizzle =====================
+    // Item e = (k-quad j, column c), e = j * C + c: consecutive threads read consecutive addresses of the BK x C block of
+    // X (one contiguous run of BK * C floats, L2 resident: 20 row tiles share it) and write one 16-byte unit of row c
+    // (X_hi) and of row CP + c (X_lo).  Values are prefetched one k-block ahead in registers.
+    if (p.xmode == 1) {
+      constexpr int NQ = BK / 4;
+      constexpr int NI = (48 * NQ + 63) / 64;
+      const int tid2 = threadIdx.x - 64;
+      const int C = (int)p.C;
+      const int nitems = C * NQ;
+      uint32_t off[NI];
+      int jq[NI], cc[NI];
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int e = tid2 + 64 * i;
+        const int j = e / C, c = e - j * C;
+        jq[i] = (e < nitems) ? j : -1;
+        cc[i] = c;
+        const uint32_t sw = (BK == 32) ? (uint32_t)(c & 7) : (uint32_t)((c >> 1) & 3);
+        off[i] = (uint32_t)c * ROW_BYTES + ((((uint32_t)j) ^ sw) << 4);  // CP % 8 == 0: rows c and CP + c swizzle alike
+      }
+      const int64_t my_tiles = (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+      const int64_t total = my_tiles * nkb;
+      float xa[NI][4], xb[NI][4];
+      auto load_x = [&](float (&reg)[NI][4], int64_t lin) {
+        if (lin >= total) return;
+        const int64_t ti = lin / nkb;
+        const int kb = (int)(lin - ti * nkb);
+        const int64_t tile = blockIdx.x + ti * gridDim.x;
+        const int64_t b = tile / p.MT;
+        const float* Xb = p.X + b * p.K * C;
+        const int64_t k0 = (int64_t)kb * BK;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const int64_t k = k0 + 4 * jq[i] + qd;
+            reg[i][qd] = (jq[i] >= 0 && k < p.K) ? __ldg(Xb + k * C + cc[i]) : 0.f;
+          }
+        }
+      };
+      int s = 0;
+      uint32_t ph = 0;
+      auto store_x = [&](const float (&reg)[NI][4]) {
+        mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+        unsigned char* xt = sRing + s * stage_bytes + A_STAGE;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          if (jq[i] >= 0) {
+            uint4 h, l;
+            uint32_t* hp = reinterpret_cast<uint32_t*>(&h);
+            uint32_t* lp = reinterpret_cast<uint32_t*>(&l);
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+              const uint32_t hb = (__float_as_uint(reg[i][qd]) + 0x1000u) & 0xFFFFE000u;
+              hp[qd] = hb;
+              lp[qd] = (__float_as_uint(reg[i][qd] - __uint_as_float(hb)) + 0x1000u) & 0xFFFFE000u;
+            }
+            *reinterpret_cast<uint4*>(xt + off[i]) = h;
+            *reinterpret_cast<uint4*>(xt + off[i] + p.CP * ROW_BYTES) = l;
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&x_full[s]));
+        if (++s == p.SA) { s = 0; ph ^= 1; }
+      };
+      load_x(xa, 0);
+      for (int64_t lin = 0; lin < total; lin += 2) {
+        load_x(xb, lin + 1);
+        store_x(xa);
+        if (lin + 1 < total) {
+          load_x(xa, lin + 2);
+          store_x(xb);
+        }
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -338,11 +437,15 @@ struct D2Config {
   int sa;    // ring depth (0 = deepest that fits)
   int grid;  // 0 = one CTA per SM
   int dbg;
+  int xmode; // 0: pre-split workspace + TMA (default); 1: X operand produced in the kernel by warps 2-3: needs no
+             // workspace but is ~1.8x slower (two warps cannot hide the L2 latency of the strided X reads) -- used when
+             // the caller passes no workspace
 };
 
 static D2Config d2_default_config() {
   static D2Config cfg = [] {
-    D2Config c{32, 0, 0, 0};
+    D2Config c{32, 0, 0, 0, 0};
+    if (const char* e = getenv("LOB_D2_XMODE")) c.xmode = atoi(e);
     if (const char* e = getenv("LOB_D2_BK")) c.bk = atoi(e);
     if (const char* e = getenv("LOB_D2_SA")) c.sa = atoi(e);
     if (const char* e = getenv("LOB_D2_GRID")) c.grid = atoi(e);
@@ -369,8 +472,9 @@ int dense_matmul_stream2_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, con
   if (C > 48 || C < 1) return LOB_ERR_UNSUPPORTED;
   if ((lda % 4) != 0 || (a_bs % 4) != 0 || (reinterpret_cast<uintptr_t>(A) & 15) != 0) return LOB_ERR_UNSUPPORTED;
   if (M >= (1LL << 31) || K >= (1LL << 31) || B >= (1LL << 31)) return LOB_ERR_UNSUPPORTED;
-  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15) != 0 || ws_bytes < dense_stream2_workspace_bytes(B, K, C))
-    return LOB_ERR_UNSUPPORTED;
+  const bool have_ws = ws && (reinterpret_cast<uintptr_t>(ws) & 15) == 0 &&
+                       ws_bytes >= dense_stream2_workspace_bytes(B, K, C);
+  const int xmode = (cfg.xmode || !have_ws) ? 1 : 0;
   if ((d || dots) && !E && M != K) return LOB_ERR_UNSUPPORTED;
   PFN_encodeTiled_d2 enc = d2_encode_fn();
   if (!enc) return LOB_ERR_UNSUPPORTED;
@@ -387,11 +491,15 @@ int dense_matmul_stream2_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, con
     cuuint32_t box[3] = {(cuuint32_t)BK, D2_ROWS, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(A), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                     (cfg.dbg & 32) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                    : ((cfg.dbg & 64) ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B),
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return LOB_ERR_UNSUPPORTED;
   }
-  {
+  if (xmode == 1) {
+    tmX = tmA;  // unused by the kernel
+  } else {
     cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)(2 * CP), (cuuint64_t)B};
     cuuint64_t gstr[2] = {(cuuint64_t)Kp * 4, (cuuint64_t)(2 * CP) * Kp * 4};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(2 * CP), 1};
@@ -402,7 +510,7 @@ int dense_matmul_stream2_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, con
     if (r != CUDA_SUCCESS) return LOB_ERR_UNSUPPORTED;
   }
 
-  if (!(cfg.dbg & 128)) {
+  if (xmode == 0 && !(cfg.dbg & 128)) {
     dim3 grid((unsigned)cdiv(Kp, SPLIT2_KT), (unsigned)B);
     const size_t sm = (size_t)SPLIT2_KT * ((int)C | 1) * sizeof(float);
     k_split_x2<<<grid, 256, sm, st>>>(X, (float*)ws, K, Kp, (int)C, CP);
@@ -420,6 +528,7 @@ int dense_matmul_stream2_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, con
 
   D2Params p;
   p.Y = Y;
+  p.X = X;
   p.E = E ? E : X;
   p.alpha = alpha;
   p.alpha_bs = alpha_bs;
@@ -442,6 +551,7 @@ int dense_matmul_stream2_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, con
   // which only adds the (otherwise dropped, O(2^-22)) a_lo * x_lo terms of those columns
   p.idesc_lo = ds::make_idesc_tf32(128, (CP + 15) / 16 * 16);
   p.dbg = cfg.dbg;
+  p.xmode = xmode;
   const int64_t grid = std::min<int64_t>(p.ntiles, cfg.grid > 0 ? cfg.grid : kNumSMs);
   if (BK == 32) {
     auto kern = k_dense_stream2<32>;

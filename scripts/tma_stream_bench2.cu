@@ -27,6 +27,13 @@ __device__ __forceinline__ void tma3(uint32_t dst, const CUtensorMap* m, uint32_
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+__global__ void k_fill_rand(float* p, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned long long x = i * 0x9E3779B97F4A7C15ULL; x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33;
+    p[i] = (float)(unsigned)(x >> 40) * (1.0f / 8388608.0f) - 1.0f;
+  }
+}
+
 struct P {
   int cols, rows, nstage, hops, spin_warps, xrows, nkb, tiles_per_batch, ntiles;
 };
@@ -93,7 +100,8 @@ int main(int argc, char** argv) {
   cudaMalloc(&A, B * N * N * 4);
   cudaMalloc(&X, B * 128 * N * 4);
   cudaMalloc(&sink, 4);
-  cudaMemset(A, 0x3c, B * N * N * 4);
+  if (argc > 1) { k_fill_rand<<<1184, 256>>>(A, (size_t)B * N * N); printf("operator filled with random data\n"); }
+  else cudaMemset(A, 0x3c, B * N * N * 4);
   cudaMemset(X, 0x3c, B * 128 * N * 4);
   void* fp = nullptr;
   cudaDriverEntryPointQueryResult q;
@@ -101,11 +109,8 @@ int main(int argc, char** argv) {
   PFN enc = (PFN)fp;
   cudaFuncSetAttribute(k_stream2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   struct Cfg { int cols, nstage, hops, spin, xrows; } cfgs[] = {
-      {32, 5, 1, 0, 0},  {32, 4, 1, 0, 0},  {32, 3, 1, 0, 0},  {32, 2, 1, 0, 0},  {32, 6, 1, 0, 0},
-      {16, 12, 1, 0, 0}, {16, 10, 1, 0, 0}, {16, 8, 1, 0, 0},  {16, 6, 1, 0, 0},  {16, 4, 1, 0, 0},
-      {32, 5, 2, 0, 0},  {32, 5, 3, 0, 0},  {32, 5, 1, 8, 0},  {32, 5, 1, 14, 0}, {32, 5, 3, 12, 0},
-      {32, 5, 1, 0, 80}, {32, 4, 1, 0, 80}, {32, 3, 1, 0, 80}, {16, 8, 1, 0, 80}, {16, 10, 1, 0, 80},
-      {32, 3, 3, 12, 80}, {16, 8, 3, 12, 80}};
+      {32, 5, 1, 0, 0},  {32, 4, 1, 0, 0},  {32, 3, 1, 0, 0},  {16, 8, 1, 0, 0},
+      {32, 5, 1, 0, 80}, {32, 4, 1, 0, 80}, {32, 5, 3, 12, 80}};
   for (auto c : cfgs) {
     CUtensorMap tm, tmx;
     const int rows = 256;
