@@ -50,6 +50,10 @@ struct D2Params {
   int64_t ntiles;
   int a_shared;
   uint32_t idesc_hi, idesc_lo;
+  int acc_stride;  // TMEM columns per accumulator
+  int slot_base;   // first A_lo operand slot column
+  int nslot;       // A_lo operand slots (each 2 * BK columns)
+  int acc_bufs;    // 2: accumulators double-buffered (epilogue overlaps the next tile); 1: single, more operand slots
   int xmode;     // 0: X operand tiles TMA-loaded from the pre-split workspace; 1: produced in the kernel (warps 2-3)
   int dbg;       // harness experiments: 1 skip lo MMA, 2 skip conversion, 4 skip all MMAs
 };
@@ -59,7 +63,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1)
 k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX, D2Params p) {
   using namespace ds;
   constexpr int A_STAGE = D2_ROWS * BK * 4;
-  constexpr int NSLOT = 128 / (2 * BK);  // A_lo operand slots in TMEM (each: 2 M tiles x BK columns)
+  const int NSLOT = p.nslot;  // A_lo operand slots in TMEM (each: 2 M tiles x BK columns)
   constexpr int ROW_BYTES = BK * 4;
   constexpr int NU = BK / 4;  // 16-byte units per operator row
 
@@ -73,8 +77,8 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* empty = full + D2_MAX_ST;       // [MAX_ST] MMA (commit) -> TMA
   uint64_t* x_full = empty + D2_MAX_ST;     // [MAX_ST] X producers -> MMA (xmode 1)
   uint64_t* lo_full = x_full + D2_MAX_ST;   // [NSLOT]  converters -> MMA
-  uint64_t* lo_empty = lo_full + 4;         // [NSLOT]  MMA (commit) -> converters
-  uint64_t* acc_full = lo_empty + 4;        // [2]
+  uint64_t* lo_empty = lo_full + 8;         // [NSLOT]  MMA (commit) -> converters
+  uint64_t* acc_full = lo_empty + 8;        // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -153,9 +157,10 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int s = 0, sl = 0;
     uint32_t ph = 0, phl = 0, it = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const uint32_t buf = it & 1;
-      mbar_wait(smem_u32(&acc_empty[buf]), ((it >> 1) & 1) ^ 1);
-      const uint32_t d0 = tmem_base + buf * 2 * D2_ACC_COLS;
+      const uint32_t buf = (p.acc_bufs == 2) ? (it & 1) : 0u;
+      const uint32_t accph = (p.acc_bufs == 2) ? ((it >> 1) & 1) : (it & 1);
+      mbar_wait(smem_u32(&acc_empty[buf]), accph ^ 1);
+      const uint32_t d0 = tmem_base + buf * 2 * p.acc_stride;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(smem_u32(&full[s]), ph);
         if (p.xmode == 1) mbar_wait(smem_u32(&x_full[s]), ph);
@@ -165,11 +170,11 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(sRing + s * stage_bytes);
           const uint64_t xdesc = make_kmajor_desc<BK>(a_addr + A_STAGE);
-          const uint32_t lo_slot = tmem_base + D2_SLOT_BASE + sl * (2 * BK);
+          const uint32_t lo_slot = tmem_base + p.slot_base + sl * (2 * BK);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const uint64_t adesc = make_kmajor_desc<BK>(a_addr + t * (128 * ROW_BYTES));
-            const uint32_t d_addr = d0 + t * D2_ACC_COLS;
+            const uint32_t d_addr = d0 + t * p.acc_stride;
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
               const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 8 tf32 = 32 bytes inside the swizzle span
@@ -272,15 +277,16 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int et = threadIdx.x - 128;  // 0..127 inside the epilogue group
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const uint32_t buf = it & 1;
+      const uint32_t buf = (p.acc_bufs == 2) ? (it & 1) : 0u;
+      const uint32_t accph = (p.acc_bufs == 2) ? ((it >> 1) & 1) : (it & 1);
       const int64_t b = tile / p.MT;
       const int mt = (int)(tile - b * p.MT);
       const int64_t m0 = (int64_t)mt * D2_ROWS;
       const float alpha_b = p.alpha ? p.alpha[b * p.alpha_bs] : 1.0f;
       const float* Eb = p.E + b * p.M * C;
       float* Yb = p.Y + b * p.M * C;
-      double* red = dred + buf * (2 * 4 * 48);
-      mbar_wait(smem_u32(&acc_full[buf]), (it >> 1) & 1);
+      double* red = dred + (it & 1) * (2 * 4 * 48);
+      mbar_wait(smem_u32(&acc_full[buf]), accph);
       __syncwarp();
       tc_fence_after();
 #pragma unroll 1
@@ -288,7 +294,7 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int64_t row = m0 + t * 128 + q * 32 + lane;
         const bool rok = row < p.M;
         const float dv = (p.dg && rok) ? __ldg(p.dg + b * p.d_bs + row * p.d_st) : 0.f;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + t) * D2_ACC_COLS;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + t) * p.acc_stride;
 #pragma unroll 1
         for (int c0 = 0; c0 < CP; c0 += 16) {
           float e[16];
@@ -334,7 +340,7 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int t = (warp - 8) >> 2;
     const int row = t * 128 + q * 32 + lane;
     const uint32_t swz = (BK == 32) ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + D2_SLOT_BASE + t * BK;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + p.slot_base + t * BK;
     int s = 0, sl = 0;
     uint32_t ph = 0, phl = 0;
     for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -433,6 +439,7 @@ static PFN_encodeTiled_d2 d2_encode_fn() {
 }
 
 struct D2Config {
+  int acc_bufs;  // 0/2: double-buffered accumulators; 1: single (more A_lo operand slots in TMEM)
   int bk;    // 16 (SWIZZLE_64B) or 32 (SWIZZLE_128B)
   int sa;    // ring depth (0 = deepest that fits)
   int grid;  // 0 = one CTA per SM
@@ -444,7 +451,8 @@ struct D2Config {
 
 static D2Config d2_default_config() {
   static D2Config cfg = [] {
-    D2Config c{32, 0, 0, 0, 0};
+    D2Config c{0, 32, 0, 0, 0, 0};
+    if (const char* e = getenv("LOB_D2_ACC_BUFS")) c.acc_bufs = atoi(e);
     if (const char* e = getenv("LOB_D2_XMODE")) c.xmode = atoi(e);
     if (const char* e = getenv("LOB_D2_BK")) c.bk = atoi(e);
     if (const char* e = getenv("LOB_D2_SA")) c.sa = atoi(e);
@@ -552,6 +560,11 @@ int dense_matmul_stream2_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, con
   p.idesc_lo = ds::make_idesc_tf32(128, (CP + 15) / 16 * 16);
   p.dbg = cfg.dbg;
   p.xmode = xmode;
+  p.acc_bufs = (cfg.acc_bufs == 1) ? 1 : 2;
+  p.acc_stride = 2 * CP;
+  p.slot_base = 2 * p.acc_bufs * p.acc_stride;
+  p.nslot = (512 - p.slot_base) / (2 * BK);
+  if (p.nslot > 8) p.nslot = 8;
   const int64_t grid = std::min<int64_t>(p.ntiles, cfg.grid > 0 ? cfg.grid : kNumSMs);
   if (BK == 32) {
     auto kern = k_dense_stream2<32>;

@@ -14,6 +14,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <type_traits>
+
 #include "common.cuh"
 #include "simt_tile.cuh"
 
@@ -213,6 +216,12 @@ static int launch_nn(int64_t B, int64_t M, int64_t K, int64_t C, const T* A, int
   return check_launch("k_matmul_nn");
 }
 
+// tn_skinny.cu: register-tiled kernel for the fp32 Q^T r shape (I <= 128, J <= 48)
+bool tn_skinny_applicable(int64_t N, int64_t I, int64_t J, const void* P, int64_t p_bs);
+int tn_skinny_nsplit(int64_t B, int64_t N);
+int launch_tn_skinny_f32(int64_t B, int64_t N, int64_t I, int64_t J, const float* P, int64_t p_bs, const float* Q,
+                         int64_t q_bs, float* partial, int nsplit, cudaStream_t st);
+
 struct TnPlan {
   int rn, nblk_i, nblk_j, nsplit;
   int64_t rows_per_split;
@@ -238,6 +247,19 @@ static int launch_tn(int64_t B, int64_t N, int64_t I, int64_t J, const T* P, int
                      OUT* out, void* ws, cudaStream_t st) {
   TnPlan p = tn_plan(B, N, I, J);
   ACC* partial = (ACC*)ws;
+  if constexpr (std::is_same<T, float>::value && std::is_same<ACC, float>::value) {
+    if (!getenv("LOB_DISABLE_TN_SKINNY") && tn_skinny_applicable(N, I, J, P, p_bs)) {
+      // the workspace is sized for max(generic plan, skinny plan) splits (lob_tn_matmul_workspace_bytes)
+      const int ns = tn_skinny_nsplit(B, N);
+      int s = launch_tn_skinny_f32(B, N, I, J, P, p_bs, Q, q_bs, partial, ns, st);
+      if (s == LOB_OK) {
+        const int64_t per = I * J;
+        k_reduce_splits<ACC, OUT><<<(unsigned)cdiv(B * per, 256), 256, 0, st>>>(per, ns, partial, out, B);
+        return check_launch("k_reduce_splits");
+      }
+      if (s != LOB_ERR_UNSUPPORTED) return s;
+    }
+  }
   dim3 grid((unsigned)p.nsplit, (unsigned)B, (unsigned)(p.nblk_i * p.nblk_j));
 #define LOB_TN_CASE(R)                                                                                              \
   case R:                                                                                                           \
@@ -369,7 +391,8 @@ extern "C" int lob_dense_matmul(int32_t dtype, int64_t B, int64_t M, int64_t K, 
 extern "C" size_t lob_tn_matmul_workspace_bytes(int64_t B, int64_t N, int64_t I, int64_t J) {
   if (B <= 0 || N <= 0 || I <= 0 || J <= 0) return 0;
   TnPlan p = tn_plan(B, N, I, J);
-  return (size_t)B * p.nsplit * I * J * sizeof(double);
+  const int ns = std::max(p.nsplit, tn_skinny_nsplit(B, N));
+  return (size_t)B * ns * I * J * sizeof(double);
 }
 
 extern "C" int lob_tn_matmul(int32_t dtype, int32_t out_dtype, int64_t B, int64_t N, int64_t I, int64_t J,

@@ -1,0 +1,161 @@
+// tn_skinny.cu -- Out (B, I, J) = P^T Q for tall-skinny fp32 operands P (B, N, I), Q (B, N, J) with I <= 128, J <= 48:
+// the Q^T r product of the pivoted-Cholesky preconditioner apply (operators/added_diag_linear_operator.py:137; I = rank,
+// J = probe + rhs columns, N = operator size), once per CG iteration.
+//
+// This contraction stays on the CUDA cores on purpose: the tensor core truncates (does not round) when it adds into its
+// fp32 accumulator, a systematic bias ~1.5e-8 * N that the preconditioner amplifies by lambda_max / sigma^2 into the
+// log-determinant; FFMA accumulation rounds to nearest.  The generic kernel in matmul_simt.cu reached only
+// 8.7 TFLOP/s on this shape (3.8 ms at config 2); this one is register-tiled for it:
+//   * one CTA = one (batch element, row split): 8 x 4 outputs per thread, threads laid out (I/8) x (J/4)  (13 x 9 = 117
+//     of 128 threads for I = 100, J = 33), every thread walks all rows of the split;
+//   * operands staged with cp.async (16-byte chunks of P rows, 4-byte elements of the odd-length Q rows, zero-fill past
+//     the split) into a double-buffered shared-memory tile of 32 rows;
+//   * per row and thread: 3 LDS.128 (two 4-wide chunks of the P row -- chunk t and chunk t + half, so consecutive
+//     threads read consecutive 16-byte words -- and one chunk of the Q row) for 32 FFMA;
+//   * per-split partial sums are combined in double by k_reduce_splits (matmul_simt.cu): deterministic.
+#include "common.cuh"
+
+namespace lob {
+
+constexpr int TNS_TK = 32;       // rows per shared-memory tile
+constexpr int TNS_MAX_I = 128;
+constexpr int TNS_MAX_J = 48;
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// LDP = 8 * half (padded I), LDQ = 4 * nj (padded J); blockDim.x = round_up(half * nj, 32)
+__global__ void __launch_bounds__(256)
+k_tn_skinny(int64_t N, int I, int J, const float* __restrict__ P, int64_t p_bs, const float* __restrict__ Q,
+            int64_t q_bs, float* __restrict__ partial, int nsplit, int64_t rows_per_split, int half, int nj) {
+  extern __shared__ __align__(16) float tns_smem[];
+  const int LDP = 8 * half, LDQ = 4 * nj;
+  float* Ps = tns_smem;                       // [2][TK][LDP]
+  float* Qs = tns_smem + 2 * TNS_TK * LDP;    // [2][TK][LDQ]
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int64_t b = blockIdx.y;
+  const int split = blockIdx.x;
+  const int64_t n_begin = (int64_t)split * rows_per_split;
+  const int64_t n_end = min(n_begin + rows_per_split, N);
+  const float* Pb = P + b * p_bs;
+  const float* Qb = Q + b * q_bs;
+
+  // padding columns are never written by cp.async: zero both stages once
+  for (int e = tid; e < 2 * TNS_TK * (LDP + LDQ); e += nthr) tns_smem[e] = 0.f;
+  __syncthreads();
+
+  const int pchunks = (I + 3) / 4;           // 16-byte chunks per P row (I % 4 == 0 is required by the launcher)
+  const uint32_t ps_base = (uint32_t)__cvta_generic_to_shared(Ps);
+  const uint32_t qs_base = (uint32_t)__cvta_generic_to_shared(Qs);
+  auto load_tile = [&](int stage, int64_t n0) {
+    const int total_p = TNS_TK * pchunks;
+    for (int e = tid; e < total_p; e += nthr) {
+      const int kk = e / pchunks, ch = e - kk * pchunks;
+      const bool ok = n0 + kk < n_end;
+      const float* src = Pb + (ok ? (n0 + kk) : n_begin) * I + ch * 4;
+      cp_async_16(ps_base + (uint32_t)(((stage * TNS_TK + kk) * LDP + ch * 4) * 4), src, ok ? 16u : 0u);
+    }
+    const int total_q = TNS_TK * J;
+    for (int e = tid; e < total_q; e += nthr) {
+      const int kk = e / J, jj = e - kk * J;
+      const bool ok = n0 + kk < n_end;
+      const float* src = Qb + (ok ? (n0 + kk) : n_begin) * J + jj;
+      cp_async_4(qs_base + (uint32_t)(((stage * TNS_TK + kk) * LDQ + jj) * 4), src, ok ? 4u : 0u);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int ti = tid % half, tj = tid / half;
+  const bool active = tj < nj;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int64_t ntile = (n_end - n_begin + TNS_TK - 1) / TNS_TK;
+  if (ntile > 0) load_tile(0, n_begin);
+  for (int64_t t = 0; t < ntile; ++t) {
+    const int stage = (int)(t & 1);
+    if (t + 1 < ntile) {
+      load_tile(stage ^ 1, n_begin + (t + 1) * TNS_TK);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (active) {
+      const float* prow = Ps + stage * TNS_TK * LDP + ti * 4;
+      const float* qrow = Qs + stage * TNS_TK * LDQ + tj * 4;
+#pragma unroll 8
+      for (int kk = 0; kk < TNS_TK; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(prow + kk * LDP);
+        const float4 a1 = *reinterpret_cast<const float4*>(prow + kk * LDP + half * 4);
+        const float4 q4 = *reinterpret_cast<const float4*>(qrow + kk * LDQ);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], q[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+
+  if (active) {
+    float* out = partial + ((b * nsplit + split) * I) * J;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ii = (i < 4) ? (ti * 4 + i) : ((half + ti) * 4 + i - 4);
+      if (ii >= I) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int jj = tj * 4 + j;
+        if (jj < J) out[ii * J + jj] = acc[i][j];
+      }
+    }
+  }
+}
+
+bool tn_skinny_applicable(int64_t N, int64_t I, int64_t J, const void* P, int64_t p_bs) {
+  return I >= 8 && I <= TNS_MAX_I && (I % 4) == 0 && J >= 1 && J <= TNS_MAX_J && N >= 256 && (p_bs % 4) == 0 &&
+         (reinterpret_cast<uintptr_t>(P) & 15) == 0;
+}
+
+// row splits: enough CTAs for ~5 full waves of the resident-CTA capacity, at least 128 rows each
+int tn_skinny_nsplit(int64_t B, int64_t N) {
+  const int64_t slots = (int64_t)kNumSMs * 6;
+  int64_t ns = cdiv(5 * slots, B);
+  const int64_t maxs = std::max<int64_t>(1, N / 128);
+  if (ns > maxs) ns = maxs;
+  if (ns > 64) ns = 64;
+  if (ns < 1) ns = 1;
+  const int64_t rps = cdiv(N, ns);
+  return (int)cdiv(N, rps);
+}
+
+int launch_tn_skinny_f32(int64_t B, int64_t N, int64_t I, int64_t J, const float* P, int64_t p_bs, const float* Q,
+                         int64_t q_bs, float* partial, int nsplit, cudaStream_t st) {
+  const int pchunks = (int)((I + 3) / 4);
+  const int half = (pchunks + 1) / 2;
+  const int nj = (int)((J + 3) / 4);
+  const int nthr = (int)align_up((size_t)half * nj, 32);
+  if (nthr > 256) return LOB_ERR_UNSUPPORTED;
+  const int64_t rows_per_split = cdiv(N, nsplit);
+  const size_t smem = (size_t)2 * TNS_TK * (8 * half + 4 * nj) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LOB_CUDA(cudaFuncSetAttribute(k_tn_skinny, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)nsplit, (unsigned)B);
+  k_tn_skinny<<<grid, nthr, smem, st>>>(N, (int)I, (int)J, P, p_bs, Q, q_bs, partial, nsplit, rows_per_split, half, nj);
+  return check_launch("k_tn_skinny");
+}
+
+}  // namespace lob

@@ -26,7 +26,7 @@ int dense_matmul_stream_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, cons
                                 const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
                                 cudaStream_t st, DsConfig cfg);
 struct D2Config {
-  int bk, sa, grid, dbg, xmode;
+  int acc_bufs, bk, sa, grid, dbg, xmode;
 };
 size_t dense_stream2_workspace_bytes(int64_t B, int64_t K, int64_t C);
 int dense_matmul_stream2_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
@@ -43,7 +43,7 @@ static int launch(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, in
                   float* Y, const float* E, const float* alpha, int64_t alpha_bs, const float* d, int64_t d_bs,
                   int64_t d_st, double* dots, void* ws, size_t wsb, lob::DsConfig cfg) {
   if (g_impl == 2) {
-    lob::D2Config c2{cfg.bk, cfg.sa, cfg.grid, cfg.dbg, cfg.lo_mode};  // lo_mode slot carries xmode for generation 2
+    lob::D2Config c2{(cfg.dbg & 1024) ? 1 : 2, cfg.bk, cfg.sa, cfg.grid, cfg.dbg, cfg.lo_mode};  // lo_mode slot carries xmode for generation 2
     return lob::dense_matmul_stream2_f32_cfg(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots,
                                              ws, wsb, 0, c2);
   }
@@ -254,7 +254,7 @@ int main(int argc, char** argv) {
 
   // ---------------- 1. fp32 -> tf32 conversion model of the tensor core ----------------
   for (int bk : {16, 32}) {
-    if (g_impl == 2) break;
+    if (g_impl >= 2) break;
     Case cs{1, 256, 512, 16, false, false, false, false};
     double de, me[2];
     int st;
@@ -269,7 +269,7 @@ int main(int argc, char** argv) {
     Case cs{1, 256, K, 16, false, false, false, false};
     double de;
     int st;
-    lob::DsConfig cfg{16, 0, 0, g_impl == 2 ? 1 : 0, 0, 0};
+    lob::DsConfig cfg{g_impl == 3 ? 0 : 16, 0, 0, g_impl == 2 ? 1 : 0, 0, 0};
     const double err = run_case(cs, cfg, 64, &de, &st);
     printf("[bias] all-positive data K=%lld: normalised err %.3e\n", (long long)K, err);
     g_positive = false;
@@ -286,11 +286,12 @@ int main(int argc, char** argv) {
   for (int bk : {16, 32}) {
     for (int lo : {0, 1}) {
       for (const Case& cs : cases) {
-        if (lo == 1 && g_impl != 2 && !(cs.M == 700)) continue;  // the other conversion model on one shape only
-        if (g_impl == 2 && cs.C > 48) continue;
+        if (lo == 1 && g_impl != 2 && !(cs.M == 700 && g_impl == 1)) continue;  // other conversion model: one shape
+        if (g_impl >= 2 && cs.C > 48) continue;
+        if (g_impl == 3 && bk == 16) continue;
         double de;
         int st;
-        lob::DsConfig cfg{bk, 0, 0, lo, 0, 0};
+        lob::DsConfig cfg{g_impl == 3 ? 0 : bk, 0, 0, (g_impl == 2) ? 0 : lo, 0, (g_impl == 2 && lo == 1) ? 1024 : 0};
         const double err = run_case(cs, cfg, 40, &de, &st);
         const bool ok = (lo == 1 && g_impl != 2) || (err < 2e-6 && de < 1e-12);
         if (!ok) ++failures;
@@ -325,10 +326,14 @@ int main(int argc, char** argv) {
     };
     const V variants1[] = {{16, 0, 3, 0, 0}, {32, 0, 2, 0, 0}};
     // generation 2: {bk, sa, xmode (in the sl slot), grid, dbg}
-    const V variants2[] = {{32, 0, 0, 0, 0},   {16, 0, 0, 0, 0},   {32, 0, 0, 0, 1},   {32, 0, 0, 0, 2},   {32, 0, 0, 0, 4},
-                           {32, 0, 0, 0, 6},   {32, 4, 0, 0, 0},   {32, 3, 0, 0, 0},   {32, 0, 0, 0, 128}, {32, 0, 1, 0, 0}};
+    const V variants2[] = {{32, 0, 0, 0, 0},   {32, 0, 0, 0, 1024}, {16, 0, 0, 0, 0},   {16, 0, 0, 0, 1024}, {32, 4, 0, 0, 1024},
+                           {32, 0, 0, 0, 1024 + 1}, {32, 0, 0, 0, 1024 + 2}, {32, 0, 0, 0, 1024 + 128}};
+    // generation 3: {sa (bk slot unused -> 0), sa, sx, grid, dbg}
+    const V variants3[] = {{0, 0, 0, 0, 0}, {0, 4, 0, 0, 0}, {0, 3, 0, 0, 0}, {0, 5, 3, 0, 0}, {0, 0, 0, 0, 1},
+                           {0, 0, 0, 0, 2}, {0, 0, 0, 0, 4}, {0, 0, 0, 0, 6}, {0, 0, 0, 0, 128}};
     std::vector<V> variants;
-    if (g_impl == 2) variants.assign(variants2, variants2 + sizeof(variants2) / sizeof(V));
+    if (g_impl == 3) variants.assign(variants3, variants3 + sizeof(variants3) / sizeof(V));
+    else if (g_impl == 2) variants.assign(variants2, variants2 + sizeof(variants2) / sizeof(V));
     else variants.assign(variants1, variants1 + sizeof(variants1) / sizeof(V));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
