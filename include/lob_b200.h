@@ -239,6 +239,23 @@ size_t lob_cap_solve_workspace_bytes(int64_t B, int32_t k, int64_t C);
 int lob_cap_solve(int32_t dtype, int64_t B, int32_t k, int64_t C, const double* G, int64_t g_batch_stride, void* W,
                   void* logdet_cap, int32_t* info, void* ws, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Lanczos tridiagonalisation with full re-orthogonalisation (utils/lanczos.py:9-164), one fused kernel per iteration.
+ * q_mat (t_cap, B, N, C) and t_mat (t_cap, t_cap, B, C) are the reference's own work arrays (zero-initialised by the
+ * caller); w (B, N, C) = A q_k is the closure product of the current iteration.
+ *   lob_lanczos_init : q_mat[0] = init / ||init||                                            (lanczos.py:83-84)
+ *   lob_lanczos_step : mode 0 (k = 0): alpha_0, beta_0, q_1                                  (:86-100)
+ *                      mode 1 (k >= 1): alpha_k and, unless k is the last iteration, r, one Gram-Schmidt pass against
+ *                                       q_0..q_k, beta_k, q_{k+1}                             (:103-131, :153)
+ *                      mode 2: one more re-orthogonalisation of q_{k+1}                       (:141-147)
+ * flags (2 x int32, device): [0] some <q_j, q_{k+1}> > tol (signed, as the reference :133,:147) -- rewritten by every
+ * mode 1 / 2 launch; [1] some |beta_k| > 1e-6 (:150) -- rewritten by mode 0 / 1.  The host reads them to take the
+ * reference's own control decisions.
+ * ---------------------------------------------------------------------------------------------------------- */
+int lob_lanczos_init(int32_t dtype, int64_t B, int64_t N, int64_t C, const void* init, void* q0, void* stream);
+int lob_lanczos_step(int32_t dtype, int32_t mode, int64_t B, int64_t N, int64_t C, int32_t t_cap, int32_t k,
+                     const void* w, void* q_mat, void* t_mat, int32_t* flags, double tol, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -502,3 +502,27 @@ def cap_solve(G: torch.Tensor, W: torch.Tensor):
     check(lib.lob_cap_solve(dt(W), B, k, C, ptr(Gf), g_bs, ptr(Wf), ptr(logdet), ptr(info), ptr(ws), stream(W)),
           "lob_cap_solve")
     return Wf.reshape(*batch_shape, k, C), logdet.reshape(batch_shape), info
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Lanczos with full re-orthogonalisation (utils/lanczos.py:9-164)
+# ------------------------------------------------------------------------------------------------------------
+def lanczos_init(init_vecs: torch.Tensor, q0: torch.Tensor):
+    """q0 (B, N, C) <- init_vecs / ||init_vecs||_2 column-wise."""
+    require_cuda(init_vecs, q0)
+    lib = _lib.load()
+    B, N, C = init_vecs.shape
+    check(lib.lob_lanczos_init(dt(init_vecs), B, N, C, ptr(init_vecs), ptr(q0), stream(init_vecs)), "lob_lanczos_init")
+
+
+def lanczos_step(mode: int, k: int, w: Optional[torch.Tensor], q_mat: torch.Tensor, t_mat: torch.Tensor,
+                 flags: torch.Tensor, tol: float):
+    """One fused Lanczos iteration on q_mat (T, B, N, C), t_mat (T, T, B, C); flags = int32[2] decision words."""
+    require_cuda(q_mat, t_mat, flags, w)
+    lib = _lib.load()
+    T, B, N, C = q_mat.shape
+    check(
+        lib.lob_lanczos_step(dt(q_mat), mode, B, N, C, T, k, ptr(w), ptr(q_mat), ptr(t_mat), ptr(flags), float(tol),
+                             stream(q_mat)),
+        "lob_lanczos_step",
+    )

@@ -88,6 +88,11 @@ _SIGS = {
         ctypes.c_int,
         [c_int32, c_int32, c_int64, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P],
     ),
+    "lob_lanczos_init": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, _P, _P]),
+    "lob_lanczos_step": (
+        ctypes.c_int,
+        [c_int32, c_int32, c_int64, c_int64, c_int64, c_int32, c_int32, _P, _P, _P, _P, c_double, _P],
+    ),
     "lob_pivchol_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "lob_pivchol_dense": (
         ctypes.c_int,

@@ -1,11 +1,115 @@
 """Lanczos helpers of the Krylov path (reference: utils/lanczos.py).
 
+``lanczos_tridiag`` (reference :9-164) runs one fused re-orthogonalisation kernel per iteration (csrc/lanczos.cu).
+
 ``lanczos_tridiag_to_diag`` (reference :167-189) runs on the device through ``lob_tridiag_eigh_slq`` -- the reference
 moves every T < 32 problem to CPU LAPACK (:179-180).
 """
 from __future__ import annotations
 
+import torch
+
 from .. import _kernels, settings
+
+
+def lanczos_tridiag(
+    matmul_closure,
+    max_iter,
+    dtype,
+    device,
+    matrix_shape,
+    batch_shape=torch.Size(),
+    init_vecs=None,
+    num_init_vecs=1,
+    tol=1e-5,
+):
+    """Lanczos tridiagonalisation with full re-orthogonalisation; same signature, outputs and control flow as the
+    reference (utils/lanczos.py:9-164): returns ``q_mat (num_init_vecs, *batch, N, num_iter)`` and
+    ``t_mat (num_init_vecs, *batch, num_iter, num_iter)``, the leading dimension squeezed when it is 1.
+
+    Each iteration is one closure product plus ONE fused kernel (``lob_lanczos_step``: alpha, residual, Gram-Schmidt
+    against the whole panel, beta, normalisation, orthogonality check); the host only reads the two decision words of
+    the reference's own rules -- "some <q_j, r> > tol: re-orthogonalise again, at most 10 times" (:133-147) and
+    "all |beta| <= 1e-6 or re-orthogonalisation failed: stop" (:150)."""
+    if not callable(matmul_closure):
+        raise RuntimeError(
+            "matmul_closure should be a function callable object that multiples a (Lazy)Tensor "
+            "by a vector. Got a {} instead.".format(matmul_closure.__class__.__name__)
+        )
+    batch_shape = torch.Size(batch_shape)
+    if init_vecs is None:
+        init_vecs = torch.randn(matrix_shape[-1], num_init_vecs, dtype=dtype, device=device)
+        init_vecs = init_vecs.expand(*batch_shape, matrix_shape[-1], num_init_vecs)
+    else:
+        if settings.debug.on():
+            if dtype != init_vecs.dtype:
+                raise RuntimeError(
+                    "Supplied dtype {} and init_vecs.dtype {} do not agree!".format(dtype, init_vecs.dtype)
+                )
+            if device != init_vecs.device:
+                raise RuntimeError(
+                    "Supplied device {} and init_vecs.device {} do not agree!".format(device, init_vecs.device)
+                )
+            if batch_shape != init_vecs.shape[:-2]:
+                raise RuntimeError(
+                    "batch_shape {} and init_vecs.shape {} do not agree!".format(batch_shape, init_vecs.shape)
+                )
+            if matrix_shape[-1] != init_vecs.size(-2):
+                raise RuntimeError(
+                    "matrix_shape {} and init_vecs.shape {} do not agree!".format(matrix_shape, init_vecs.shape)
+                )
+        num_init_vecs = init_vecs.size(-1)
+    _kernels.require_cuda(init_vecs)
+
+    n = matrix_shape[-1]
+    num_iter = min(max_iter, n)
+    if settings.verbose_linalg.on():
+        settings.verbose_linalg.logger.debug(
+            f"Running Lanczos on a {matrix_shape} matrix with a {init_vecs.shape} RHS for {num_iter} iterations."
+        )
+    if num_iter < 2:
+        # the reference indexes t_mat[0, 1] unconditionally (:95): same failure, raised before any work
+        raise IndexError("index 1 is out of bounds for dimension 0 with size 1")
+
+    B = 1
+    for sdim in batch_shape:
+        B *= int(sdim)
+    dev = init_vecs.device
+    init_flat = init_vecs.expand(*batch_shape, n, num_init_vecs).contiguous().reshape(B, n, num_init_vecs)
+    q_mat = torch.zeros(num_iter, B, n, num_init_vecs, dtype=dtype, device=dev)
+    t_mat = torch.zeros(num_iter, num_iter, B, num_init_vecs, dtype=dtype, device=dev)
+    flags = torch.zeros(2, dtype=torch.int32, device=dev)
+
+    def closure(qflat):
+        w = matmul_closure(qflat.reshape(*batch_shape, n, num_init_vecs))
+        return w.reshape(B, n, num_init_vecs).contiguous()
+
+    _kernels.lanczos_init(init_flat, q_mat[0])
+    _kernels.lanczos_step(0, 0, closure(q_mat[0]), q_mat, t_mat, flags, tol)
+    k = 0
+    for k in range(1, num_iter):
+        _kernels.lanczos_step(1, k, closure(q_mat[k]), q_mat, t_mat, flags, tol)
+        if (k + 1) < num_iter:
+            some_inner_above_tol, some_beta_nonzero = (int(v) for v in flags.tolist())
+            could_reorthogonalize = False
+            for _ in range(10):
+                if not some_inner_above_tol:
+                    could_reorthogonalize = True
+                    break
+                _kernels.lanczos_step(2, k, None, q_mat, t_mat, flags, tol)
+                some_inner_above_tol = int(flags[0].item())
+            if not some_beta_nonzero or not could_reorthogonalize:
+                break
+    num_iter = k + 1
+
+    nb = len(batch_shape)
+    q_out = q_mat[:num_iter].reshape(num_iter, *batch_shape, n, num_init_vecs)
+    q_out = q_out.permute(-1, *range(1, 1 + nb), -2, 0).contiguous()
+    t_out = t_mat[:num_iter, :num_iter].reshape(num_iter, num_iter, *batch_shape, num_init_vecs)
+    t_out = t_out.permute(-1, *range(2, 2 + nb), 0, 1).contiguous()
+    q_out.squeeze_(0)
+    t_out.squeeze_(0)
+    return q_out, t_out
 
 
 def lanczos_tridiag_to_diag(t_mat):
