@@ -455,6 +455,9 @@ def toeplitz_embed_fft(col: torch.Tensor):
     return torch.fft.rfft(c), L  # cuFFT R2C
 
 
+TOEPLITZ_SCRATCH_BYTES = 4.5 * 2**30  # per (B, C, L) scratch array of one batch chunk of toeplitz_matmul
+
+
 def toeplitz_matmul(col: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = None, fc_cache=None):
     """Symmetric Toeplitz matmul through a length-L (power of two >= 2N) real circulant embedding
     (utils/toeplitz.py:131-149 uses length 2N-1 complex FFTs; any L >= 2N-1 gives the same product).
@@ -469,18 +472,31 @@ def toeplitz_matmul(col: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor
         fc_cache = toeplitz_embed_fft(col)
     fc, L = fc_cache
     fc_bs = 0 if fc.shape[0] == 1 and B > 1 else fc.shape[-1]
-    xt = torch.empty(B, C, L, dtype=X.dtype, device=X.device)
-    check(lib.lob_toeplitz_pad(dt(X), B, N, C, L, ptr(Xf), ptr(xt), stream(X)), "lob_toeplitz_pad")
-    fx = torch.fft.rfft(xt)  # cuFFT R2C, batched over (B, C)
-    H = fx.shape[-1]
-    check(lib.lob_toeplitz_mul(dt(X), B, C, H, ptr(fc), fc_bs, ptr(fx), stream(X)), "lob_toeplitz_mul")
-    yt = torch.fft.irfft(fx, n=L)  # cuFFT C2R (normalised by 1/L)
     Y = torch.empty(B, N, C, dtype=X.dtype, device=X.device)
     dd, d_bs, d_st = _diag_args(d, batch_shape, N)
-    check(
-        lib.lob_toeplitz_unpad(dt(X), B, N, C, L, ptr(yt), 1.0, ptr(Xf), ptr(dd), d_bs, d_st, ptr(Y), stream(X)),
-        "lob_toeplitz_unpad",
-    )
+    # The padded transposes and the spectrum are 3 x (B, C, L) scratch: at BASELINE config 4 (B = 64, N = 2^20, 33
+    # columns) that is 53 GB per product on top of the solver state.  Batch elements are independent, so the product is
+    # done in batch chunks whose scratch stays below ~4.5 GB each (16 elements at config 4).
+    chunk = max(1, min(B, int(TOEPLITZ_SCRATCH_BYTES // (C * L * X.element_size()))))
+    for b0 in range(0, B, chunk):
+        b1 = min(B, b0 + chunk)
+        nb = b1 - b0
+        xt = torch.empty(nb, C, L, dtype=X.dtype, device=X.device)
+        check(lib.lob_toeplitz_pad(dt(X), nb, N, C, L, ptr(Xf[b0:b1]), ptr(xt), stream(X)), "lob_toeplitz_pad")
+        fx = torch.fft.rfft(xt)  # cuFFT R2C, batched over (B, C)
+        del xt
+        H = fx.shape[-1]
+        fc_c = fc if fc_bs == 0 else fc[b0:b1]
+        check(lib.lob_toeplitz_mul(dt(X), nb, C, H, ptr(fc_c), fc_bs, ptr(fx), stream(X)), "lob_toeplitz_mul")
+        yt = torch.fft.irfft(fx, n=L)  # cuFFT C2R (normalised by 1/L)
+        del fx
+        dd_c = dd if (dd is None or d_bs == 0) else dd[b0:b1]
+        check(
+            lib.lob_toeplitz_unpad(dt(X), nb, N, C, L, ptr(yt), 1.0, ptr(Xf[b0:b1]), ptr(dd_c), d_bs, d_st,
+                                   ptr(Y[b0:b1]), stream(X)),
+            "lob_toeplitz_unpad",
+        )
+        del yt
     return Y.reshape(*batch_shape, N, C)
 
 

@@ -7,7 +7,7 @@ import torch
 from .. import _kernels
 from ..utils.memoize import cached
 from .added_diag_linear_operator import AddedDiagLinearOperator
-from .diag_linear_operator import DiagLinearOperator
+from .diag_linear_operator import ConstantDiagLinearOperator, DiagLinearOperator
 from .root_linear_operator import LowRankRootLinearOperator
 
 
@@ -25,8 +25,35 @@ class LowRankRootAddedDiagLinearOperator(AddedDiagLinearOperator):
             )
         super().__init__(*linear_ops, preconditioner_override=preconditioner_override)
 
+    def _shared_root_constant_diag(self):
+        """BASELINE config 5: ONE root U (N, r) shared by the whole batch and a constant diagonal sigma_b per batch
+        element.  The reference would materialise D^-1 U as (*batch, N, r) (low_rank_root_added_diag_...py:44 through
+        diag_linear_operator.py:211-212: 40 TB at the config's sizes); here U^T D^-1 U = (U^T U) / sigma_b, the r x r
+        Gram matrix is computed once, and the two tall products become plain (batch x N) x (N x r) GEMMs that read U
+        once for the whole batch."""
+        return (self._shared_root() is not None and isinstance(self._diag_tensor, ConstantDiagLinearOperator)
+                and len(self.batch_shape) > 0)
+
+    def _shared_root(self):
+        """The (N, r) root when every batch element uses the same one (un-batched, or a stride-0 expanded view as
+        AddedDiagLinearOperator's batch broadcasting produces), else None."""
+        U = self._linear_op._root_tensor()
+        if U.dim() == 2:
+            return U
+        if all(st == 0 or sz == 1 for st, sz in zip(U.stride()[:-2], U.shape[:-2])):
+            return U[(0,) * (U.dim() - 2)]
+        return None
+
+    def _sigma(self):
+        return self._diag_tensor.diag_values.expand(*self.batch_shape, 1).reshape(-1)  # (B,)
+
     def _gram(self):
         """G = U^T D^-1 U in double, shared by ``_solve`` and ``_logdet`` (the reference caches chol(I + G), :36-47)."""
+        if getattr(self, "_gram_cache", None) is None and self._shared_root_constant_diag():
+            U = self._shared_root()
+            k = U.shape[-1]
+            g0 = _kernels.tn_matmul(U.unsqueeze(0), U.unsqueeze(0), out_dtype=torch.float64).reshape(1, k, k)
+            self._gram_cache = (g0 / self._sigma().double().reshape(-1, 1, 1)).reshape(*self.batch_shape, k, k)
         if getattr(self, "_gram_cache", None) is None:
             U = self._linear_op._root_tensor()
             d = self._diag_tensor._diag
@@ -43,6 +70,19 @@ class LowRankRootAddedDiagLinearOperator(AddedDiagLinearOperator):
     def _solve(self, rhs, preconditioner=None, num_tridiag=0):  # :62-87
         U = self._linear_op._root_tensor()
         d = self._diag_tensor._diag
+        if self._shared_root_constant_diag() and rhs.shape[-1] == 1 and rhs.shape[:-2] == self.batch_shape:
+            # x = (b - U (I + U^T U / s)^-1 U^T b / s) / s with the batch as the GEMM's row dimension.  The two products
+            # are plain dense GEMMs on contiguous operands (cuBLAS through torch.matmul), U is read once per product.
+            U = self._shared_root()
+            _kernels.require_cuda(rhs, U)
+            n, k = U.shape
+            sig = self._sigma()
+            R = rhs.reshape(-1, n)  # (B, N)
+            w = (torch.matmul(R, U) / sig.unsqueeze(-1)).unsqueeze(-1)  # U^T D^-1 b, (B, k, 1)
+            w, _, _ = _kernels.cap_solve(self._gram().reshape(-1, k, k), w)
+            S = torch.matmul(w.squeeze(-1), U.mT)  # (B, N) = (U w)^T
+            torch.sub(R, S, out=S)
+            return _kernels.scale_rows(S.reshape(*self.batch_shape, n, 1), d, "div")
         dinv_b = _kernels.scale_rows(rhs, d, "div")  # D^-1 b
         w = _kernels.tn_matmul(U, dinv_b)  # U^T D^-1 b
         w, _, _ = _kernels.cap_solve(self._gram(), w)  # (I + U^T D^-1 U)^-1 .

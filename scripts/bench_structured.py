@@ -1,0 +1,109 @@
+"""BASELINE configs 3-5 at their full single-GPU sizes (the non-headline rows of SURVEY section 8): times one cold
+inv_quad_logdet and checks size-independent properties (true residual of the solve, logdet against an exact formula where
+one exists).  Usage: python scripts/bench_structured.py [kron] [toeplitz] [lowrank]"""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import linear_operator_b200 as lo  # noqa: E402
+from linear_operator_b200 import settings  # noqa: E402
+from linear_operator_b200.operators import (  # noqa: E402
+    AddedDiagLinearOperator, DiagLinearOperator, KroneckerProductLinearOperator, LowRankRootLinearOperator,
+    ToeplitzLinearOperator,
+)
+
+dev = torch.device("cuda:0")
+which = set(sys.argv[1:]) or {"kron", "toeplitz", "lowrank"}
+
+
+def timed(fn):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return out, e0.elapsed_time(e1)
+
+
+def report(tag, op, rhs, S):
+    with settings.num_trace_samples(S), settings.max_preconditioner_size(100):
+        torch.manual_seed(1)
+        (iq, ld), ms0 = timed(lambda: op.inv_quad_logdet(rhs, logdet=True))   # cold (plans, preconditioner)
+        torch.manual_seed(1)
+        (iq, ld), ms = timed(lambda: op.inv_quad_logdet(rhs, logdet=True))
+        x, ms_solve = timed(lambda: op.solve(rhs))
+    res = ((op @ x - rhs).norm() / rhs.norm()).item()
+    iq2 = (x * rhs).sum(-2).squeeze(-1)
+    print(f"[{tag}] inv_quad_logdet {ms:.1f} ms (first call {ms0:.1f} ms), solve {ms_solve:.1f} ms, "
+          f"true residual {res:.2e}, |inv_quad - b^T x|/|.| {((iq - iq2).abs().max() / iq2.abs().max()).item():.2e}, "
+          f"logdet[0] {ld.flatten()[0].item():.6e}, peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB",
+          flush=True)
+    return iq, ld
+
+
+if "kron" in which:
+    try:
+        g = torch.Generator(device=dev).manual_seed(3)
+        fs = []
+        for _ in range(3):
+            G = torch.randn(8, 100, 100, device=dev, generator=g)
+            fs.append(G @ G.mT / 100 + 0.1 * torch.eye(100, device=dev))
+        N = 100**3
+        op = AddedDiagLinearOperator(KroneckerProductLinearOperator(*fs), DiagLinearOperator(torch.full((8, N), 0.5, device=dev)))
+        rhs = torch.randn(8, N, 1, device=dev, generator=g)
+        iq, ld = report("cfg3 kron 100^3 batch 8 fp32", op, rhs, 32)
+        # exact logdet from the factor spectra: sum_ijk log(l1_i l2_j l3_k + 0.5)
+        ev = [torch.linalg.eigvalsh(f.double()) for f in fs]
+        lam = (ev[0][:, :, None, None] * ev[1][:, None, :, None] * ev[2][:, None, None, :]).reshape(8, -1)
+        ld_exact = torch.log(lam + 0.5).sum(-1)
+        print(f"   logdet vs exact eigen formula: max rel err {((ld.double() - ld_exact).abs() / ld_exact.abs()).max().item():.2e} "
+              "(stochastic estimate, 32 probes)", flush=True)
+        del op, rhs, fs
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        print("[cfg3] FAILED:", type(e).__name__, e, flush=True)
+
+if "toeplitz" in which:
+    for B in (16, 64):
+        try:
+            torch.cuda.reset_peak_memory_stats()
+            N = 2**20
+            j = torch.arange(N, device=dev, dtype=torch.float32)
+            ls = 50.0 * (1 + torch.arange(B, device=dev, dtype=torch.float32) / 64)
+            col = torch.exp(-0.5 * (j[None, :] / ls[:, None]) ** 2)
+            op = AddedDiagLinearOperator(ToeplitzLinearOperator(col), DiagLinearOperator(torch.full((B, N), 0.5, device=dev)))
+            g = torch.Generator(device=dev).manual_seed(4)
+            rhs = torch.randn(B, N, 1, device=dev, generator=g)
+            report(f"cfg4 toeplitz N=2^20 batch {B} fp32", op, rhs, 32)
+            del op, rhs, col
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            print(f"[cfg4 batch {B}] FAILED:", type(e).__name__, str(e)[:300], flush=True)
+            torch.cuda.empty_cache()
+
+if "lowrank" in which:
+    for B, N in ((64, 10**6), (64, 10**7), (512, 10**7)):
+        try:
+            torch.cuda.reset_peak_memory_stats()
+            g = torch.Generator(device=dev).manual_seed(5)
+            U = torch.randn(N, 256, device=dev, generator=g) / 16
+            sig = 0.5 * (1 + torch.arange(B, device=dev, dtype=torch.float32) / 4096)
+            from linear_operator_b200.operators import ConstantDiagLinearOperator
+            op = LowRankRootLinearOperator(U) + ConstantDiagLinearOperator(sig.reshape(B, 1), diag_shape=N)
+            rhs = torch.randn(B, N, 1, device=dev, generator=g)
+            (iq, ld), ms0 = timed(lambda: op.inv_quad_logdet(rhs, logdet=True))
+            (iq, ld), ms = timed(lambda: op.inv_quad_logdet(rhs, logdet=True))
+            x, ms_s = timed(lambda: op.solve(rhs))
+            r = (U @ (U.mT @ x[0]) + sig[0] * x[0] - rhs[0]).norm() / rhs[0].norm()
+            print(f"[cfg5 lowrank N={N} r=256 batch {B} (one GPU's shard)] {type(op).__name__}: inv_quad_logdet {ms:.1f} ms "
+                  f"(first {ms0:.1f}), solve {ms_s:.1f} ms, residual[0] {r.item():.2e}, peak mem "
+                  f"{torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", flush=True)
+            del op, rhs, U, x
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            print(f"[cfg5 B={B} N={N}] FAILED:", type(e).__name__, str(e)[:300], flush=True)
+            torch.cuda.empty_cache()

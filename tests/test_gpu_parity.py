@@ -320,3 +320,52 @@ def test_solve_residual_property_large():
     res = (op @ x - rhs).norm() / rhs.norm()
     assert res.item() < 1e-3
     assert relerr(npy(x2), 2.5 * npy(x)) < 1e-4
+
+
+def test_toeplitz_matmul_batch_chunking_is_exact():
+    """BASELINE config 4 needs the FFT product in batch chunks (scratch); chunking must not change a bit."""
+    from linear_operator_b200 import _kernels
+
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    B, N, C = 7, 300, 5
+    col = torch.exp(-0.5 * (torch.arange(N, device=DEV) / 9.0) ** 2).repeat(B, 1) * (1 + torch.arange(B, device=DEV)[:, None])
+    X = torch.randn(B, N, C, device=DEV, generator=gen)
+    d = 0.5 + torch.rand(B, N, device=DEV, generator=gen)
+    ref = _kernels.toeplitz_matmul(col, X, d)
+    old = _kernels.TOEPLITZ_SCRATCH_BYTES
+    try:
+        _kernels.TOEPLITZ_SCRATCH_BYTES = 2 * C * 1024 * 4  # two batch elements per chunk (L = 1024)
+        out = _kernels.toeplitz_matmul(col, X, d)
+    finally:
+        _kernels.TOEPLITZ_SCRATCH_BYTES = old
+    assert torch.equal(out, ref)
+    dense = torch.stack([torch.stack([col[b].roll(i)[:N] for i in range(N)]) for b in range(B)])  # circulant rows
+    idx = (torch.arange(N, device=DEV)[:, None] - torch.arange(N, device=DEV)[None, :]).abs()
+    T = col[:, idx]
+    want = T.double() @ X.double() + d.double().unsqueeze(-1) * X.double()
+    assert relerr(npy(out), npy(want)) < 2e-5
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.float64, 1e-10), (torch.float32, 1e-4)])
+def test_lowrank_shared_root_constant_diag(dtype, rtol):
+    """BASELINE config 5's shape of problem: one root U shared by the batch, sigma_b per batch element.  The fast path
+    (Gram once, batch as the GEMM row dimension) against a dense solve / logdet of U U^T + sigma_b I."""
+    from linear_operator_b200.operators import ConstantDiagLinearOperator
+
+    gen = torch.Generator(device=DEV).manual_seed(8)
+    B, N, r = 5, 400, 7
+    U = torch.randn(N, r, device=DEV, generator=gen, dtype=dtype) / 3
+    sig = 0.5 + torch.rand(B, 1, device=DEV, generator=gen, dtype=dtype)
+    rhs = torch.randn(B, N, 1, device=DEV, generator=gen, dtype=dtype)
+    op = LowRankRootLinearOperator(U) + ConstantDiagLinearOperator(sig, diag_shape=N)
+    assert type(op).__name__ == "LowRankRootAddedDiagLinearOperator" and op._shared_root_constant_diag()
+    x = op.solve(rhs)
+    iq, ld = op.inv_quad_logdet(rhs, logdet=True)
+    dense = (U.double() @ U.double().mT).unsqueeze(0) + sig.double().unsqueeze(-1) * torch.eye(N, device=DEV, dtype=torch.float64)
+    xd = torch.linalg.solve(dense, rhs.double())
+    assert relerr(npy(x), npy(xd)) < rtol
+    assert relerr(npy(iq), npy((rhs.double() * xd).sum((-2, -1)))) < rtol
+    assert relerr(npy(ld), npy(torch.logdet(dense))) < rtol
+    # same numbers as the general (batched-root) path
+    op2 = LowRankRootLinearOperator(U.expand(B, N, r).contiguous()) + DiagLinearOperator(sig.expand(B, N).contiguous())
+    assert relerr(npy(op2.solve(rhs)), npy(x)) < rtol
