@@ -403,19 +403,27 @@ k_split_x2(const float* __restrict__ X, float* __restrict__ Xs, int64_t K, int64
   const float* src = X + (b * K + k0) * C;
   for (int e = threadIdx.x; e < kvalid * C; e += blockDim.x) xs2[(e / C) * ldx + (e % C)] = src[e];
   __syncthreads();
-  const int kk = threadIdx.x & (SPLIT2_KT - 1);
+  // each thread writes one 16-byte word (4 consecutive k of one operand row): 16 lanes cover the 64 k of a row with
+  // one contiguous 256-byte run (Kp % 4 == 0 and k0 % 64 == 0 keep the stores aligned)
+  const int q4 = threadIdx.x & 15;
   const int kw = (int)min((int64_t)SPLIT2_KT, Kp - k0);
   const int R = 2 * CP;
-  for (int r = threadIdx.x / SPLIT2_KT; r < R; r += blockDim.x / SPLIT2_KT) {
+  for (int r = threadIdx.x >> 4; r < R; r += blockDim.x >> 4) {
     const int part = r >= CP;
     const int c = r - part * CP;
-    float out = 0.f;
-    if (c < C && kk < kvalid) {
-      const float x = xs2[kk * ldx + c];
-      const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-      out = part == 0 ? hi : __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = 4 * q4 + i;
+        if (kk < kvalid) {
+          const float x = xs2[kk * ldx + c];
+          const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+          o[i] = part == 0 ? hi : __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
+        }
+      }
     }
-    if (kk < kw) Xs[(b * R + r) * Kp + k0 + kk] = out;
+    if (4 * q4 < kw) *reinterpret_cast<float4*>(Xs + (b * R + r) * Kp + k0 + 4 * q4) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 

@@ -311,9 +311,15 @@ int dense_matmul_stream2_f32(int64_t B, int64_t M, int64_t K, int64_t C, const f
                              const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
                              cudaStream_t st);
 
+// nn_skinny.cu: CUDA-core kernel for short contractions (K <= 160, C <= 40) with the fused epilogue
+bool nn_skinny_applicable(int64_t M, int64_t K, int64_t C, const void* A, int64_t lda, int64_t a_bs);
+int launch_nn_skinny_f32(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
+                         const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs, const float* d,
+                         int64_t d_bs, int64_t d_st, double* dots, cudaStream_t st);
+
 // fp32 dispatch: streaming tcgen05 kernels (need the workspace; dense_stream2.cu for C <= 48, dense_stream.cu up to
 // C = 64) -> first-generation tcgen05 kernel -> CUDA cores.
-// LOB_DENSE_IMPL = stream2 | stream | tc | simt pins one of them (diagnostics, A/B comparisons).
+// LOB_DENSE_IMPL = stream2 | stream | nnskinny | tc | simt pins one of them (diagnostics, A/B comparisons).
 static int dense_f32_tensor_paths(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
                                   const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
                                   const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
@@ -332,6 +338,15 @@ static int dense_f32_tensor_paths(int64_t B, int64_t M, int64_t K, int64_t C, co
   if (pinned_stream || (!impl && K >= 512)) {
     int s = dense_matmul_stream_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, ws,
                                     ws_bytes, st);
+    if (s != LOB_ERR_UNSUPPORTED) return s;
+  }
+  // short contractions (the preconditioner's Q t with the fused z, <r,z> epilogue): one-tile CUDA-core kernel.  Measured
+  // 2.8 - 3.3 ms at config 2 against 2.25 ms for the first-generation tensor-core kernel below, so it only runs when
+  // pinned (LOB_DENSE_IMPL=nnskinny); kept as the tested CUDA-core alternative for this shape.
+  const bool pinned_skinny = impl && !strcmp(impl, "nnskinny");
+  if (pinned_skinny && a_bs != 0 && nn_skinny_applicable(M, K, C, A, lda, a_bs) &&
+      !((d || dots) && !E && M != K)) {
+    int s = launch_nn_skinny_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, st);
     if (s != LOB_ERR_UNSUPPORTED) return s;
   }
   return dense_matmul_tc_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, st);

@@ -151,6 +151,9 @@ int launch_tn_skinny_f32(int64_t B, int64_t N, int64_t I, int64_t J, const float
   static bool attr_set = false;
   if (!attr_set) {
     LOB_CUDA(cudaFuncSetAttribute(k_tn_skinny, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    // six 36 KB CTAs per SM need the full shared-memory carve-out
+    LOB_CUDA(cudaFuncSetAttribute(k_tn_skinny, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   dim3 grid((unsigned)nsplit, (unsigned)B);

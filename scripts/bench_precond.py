@@ -32,7 +32,7 @@ def timeit(fn, reps=10):
 
 
 ref = None
-for impl in ["tc", "stream2", "stream", "simt"]:
+for impl in ["tc", "nnskinny", "stream2", "simt"]:
     os.environ["LOB_DENSE_IMPL"] = impl
     ms = timeit(lambda: _kernels.dense_matmul(Q, t, d=d, want_dots=True, E=r, alpha=alpha))
     z = _kernels.dense_matmul(Q, t, d=d, want_dots=True, E=r, alpha=alpha)[0]

@@ -15,7 +15,7 @@ from linear_operator_b200 import _kernels  # noqa: E402
 DEV = "cuda:0"
 
 
-@pytest.fixture(params=["stream2", "stream", "tc"])
+@pytest.fixture(params=["stream2", "stream", "nnskinny", "tc"])
 def impl(request):
     """Pins the fp32 tensor-core kernel through LOB_DENSE_IMPL (read by the library on every call)."""
     os.environ["LOB_DENSE_IMPL"] = request.param
