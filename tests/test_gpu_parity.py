@@ -369,3 +369,29 @@ def test_lowrank_shared_root_constant_diag(dtype, rtol):
     # same numbers as the general (batched-root) path
     op2 = LowRankRootLinearOperator(U.expand(B, N, r).contiguous()) + DiagLinearOperator(sig.expand(B, N).contiguous())
     assert relerr(npy(op2.solve(rhs)), npy(x)) < rtol
+
+
+def test_inv_quad_logdet_baseline_operator_size_vs_oracle():
+    """BASELINE config 2's operator exactly (N = 5000, 256-direction decaying spectrum + 0.5 I, fp32, 32 probes + 1 rhs =
+    33 columns, rank-100 pivoted-Cholesky preconditioner, default settings = 21 CG iterations), batch 2: the whole CUDA
+    path (streaming tcgen05 matmul, fused CG updates, preconditioner, SLQ) against the numpy oracle on identical inputs
+    and probes.  This is where the tensor core's truncating accumulate would show if it mattered: bar 1e-4 (north star)."""
+    gen = torch.Generator(device=DEV).manual_seed(1234)
+    B, N, S = 2, 5000, 32
+    W = torch.randn(B, N, 256, device=DEV, generator=gen)
+    sc = torch.logspace(0, -1.5, 256, device=DEV)
+    W = W * sc / sc.norm()
+    K = W @ W.mT
+    d = torch.full((B, N), 0.5, device=DEV)
+    rhs = torch.randn(B, N, 1, device=DEV, generator=gen)
+    probes = torch.randn(B, N, S, device=DEV, generator=gen)
+    probes = probes / probes.norm(dim=-2, keepdim=True)
+    op = Injected(DenseLinearOperator(K), DiagLinearOperator(d))
+    op.probes = probes
+    with settings.num_trace_samples(S), settings.max_preconditioner_size(100):
+        iq, ld = op.inv_quad_logdet(rhs, logdet=True)
+    iq_o, ld_o, _ = ko.dense_added_diag_inv_quad_logdet(npy(K), npy(d), npy(rhs), probes=npy(probes), precond_rank=100)
+    e_iq = np.abs(npy(iq) - iq_o) / np.abs(iq_o)
+    e_ld = np.abs(npy(ld) - ld_o) / np.abs(ld_o)
+    print(f"N=5000 vs oracle: inv_quad rel err {e_iq.max():.2e}, logdet rel err {e_ld.max():.2e}")
+    assert e_iq.max() < F32_RTOL and e_ld.max() < F32_RTOL
