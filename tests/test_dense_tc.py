@@ -80,11 +80,11 @@ def test_dense_tc_plain_tf32_would_fail(impl):
 
 
 def test_dense_tc_back_to_back_launches_are_deterministic(impl):
-    """Stress: 12 launches of a 960-CTA problem queued without host synchronisation must be bit-identical and agree
-    with the CUDA-core kernel.  Regression test for a pipeline hazard found while speeding the kernel up: variants
-    that issue tcgen05.mma within ~100 cycles of the tcgen05.st that produced their TMEM operand corrupt single rows
-    at the top of the first M tile (scripts/experimental/, DESIGN.md section "open issues"); the shipped kernel keeps
-    the slower, verified hand-off."""
+    """Stress: 12 launches of a 48 x 5000 x 5000 problem queued without host synchronisation must be bit-identical and
+    agree with the CUDA-core kernel.  Regression test for pipeline hazards of the TMEM-operand hand-off (tcgen05.st ->
+    mbarrier -> tcgen05.mma): a fast-issue variant of the first-generation kernel corrupted single rows once the tensor
+    pipe was backed up; the shipped kernels (elect.sync'd issue on a converged warp, wait::st directly behind the
+    store) must stay bit-reproducible under load."""
     import os
 
     B, N, C = 48, 5000, 33
