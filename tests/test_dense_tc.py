@@ -145,3 +145,19 @@ def test_dense_stream_accumulation_bias_on_positive_data():
     print(f"all-positive K=5000: rel err {rel:.3e}")
     assert rel < 1e-4
     assert (Y.double() <= ref * (1 + 1e-6)).all()  # truncation only ever loses magnitude
+
+
+def test_dense_matmul_operator_shared_across_batch(impl):
+    """One operator (batch 1, also as a strided view with lda > K) applied to a batch of right-hand sides: the TMA
+    descriptor pins the batch coordinate to 0 and keeps the caller's leading dimension."""
+    g = torch.Generator(device=DEV).manual_seed(9)
+    N, C, B = 768, 33, 5
+    big = torch.randn(1, N, N + 64, device=DEV, generator=g) / N**0.5
+    for A in (big[..., :N].contiguous(), big[..., :N]):
+        X = torch.randn(B, N, C, device=DEV, generator=g)
+        d = 0.1 + torch.rand(B, N, device=DEV, generator=g)
+        Y, dots, _ = _kernels.dense_matmul(A, X, d=d, want_dots=True)
+        ref = A.double() @ X.double() + d.double().unsqueeze(-1) * X.double()
+        assert ((Y.double() - ref).abs().max() / ref.abs().max()).item() < 3e-6 + 3.5e-9 * N
+        dref = (X.double() * ref).sum(-2)
+        assert ((dots.sum(1) - dref).abs().max() / dref.abs().max()).item() < 3e-6 + 3.5e-9 * N
