@@ -462,6 +462,7 @@ static D2Config d2_default_config() {
     D2Config c{0, 32, 0, 0, 0, 0};
     if (const char* e = getenv("LOB_D2_ACC_BUFS")) c.acc_bufs = atoi(e);
     if (const char* e = getenv("LOB_D2_XMODE")) c.xmode = atoi(e);
+    if (const char* e = getenv("LOB_D2_DBG")) c.dbg = atoi(e);
     if (const char* e = getenv("LOB_D2_BK")) c.bk = atoi(e);
     if (const char* e = getenv("LOB_D2_SA")) c.sa = atoi(e);
     if (const char* e = getenv("LOB_D2_GRID")) c.grid = atoi(e);

@@ -326,8 +326,8 @@ int main(int argc, char** argv) {
     };
     const V variants1[] = {{16, 0, 3, 0, 0}, {32, 0, 2, 0, 0}};
     // generation 2: {bk, sa, xmode (in the sl slot), grid, dbg}
-    const V variants2[] = {{32, 0, 0, 0, 0},   {32, 0, 0, 0, 1024}, {16, 0, 0, 0, 0},   {16, 0, 0, 0, 1024}, {32, 4, 0, 0, 1024},
-                           {32, 0, 0, 0, 1024 + 1}, {32, 0, 0, 0, 1024 + 2}, {32, 0, 0, 0, 1024 + 128}};
+    const V variants2[] = {{32, 0, 0, 0, 0}, {32, 0, 0, 0, 256}, {32, 0, 0, 0, 0}, {32, 0, 0, 0, 256}, {32, 0, 0, 0, 512},
+                           {32, 0, 0, 0, 0}, {32, 0, 0, 0, 256}};
     // generation 3: {sa (bk slot unused -> 0), sa, sx, grid, dbg}
     const V variants3[] = {{0, 0, 0, 0, 0}, {0, 4, 0, 0, 0}, {0, 3, 0, 0, 0}, {0, 5, 3, 0, 0}, {0, 0, 0, 0, 1},
                            {0, 0, 0, 0, 2}, {0, 0, 0, 0, 4}, {0, 0, 0, 0, 6}, {0, 0, 0, 0, 128}};
