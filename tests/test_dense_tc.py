@@ -161,3 +161,29 @@ def test_dense_matmul_operator_shared_across_batch(impl):
         assert ((Y.double() - ref).abs().max() / ref.abs().max()).item() < 3e-6 + 3.5e-9 * N
         dref = (X.double() * ref).sum(-2)
         assert ((dots.sum(1) - dref).abs().max() / dref.abs().max()).item() < 3e-6 + 3.5e-9 * N
+
+
+def test_dense_matmul_c_abi_without_workspace():
+    """A C-ABI caller that passes no scratch (ws = NULL) still gets a tensor-core product: the streaming kernel then
+    produces the split right-hand side inside the kernel (workspace-free mode)."""
+    from linear_operator_b200 import _lib
+    from linear_operator_b200._lib import check, dt, ptr, stream
+
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(12)
+    B, N, C = 3, 1000, 33
+    A = torch.randn(B, N, N, device=DEV, generator=g) / N**0.5
+    X = torch.randn(B, N, C, device=DEV, generator=g)
+    d = 0.1 + torch.rand(B, N, device=DEV, generator=g)
+    Y = torch.empty(B, N, C, device=DEV)
+    n_parts = int(lib.lob_dense_matmul_parts(N))
+    dots = torch.empty(B, n_parts, C, dtype=torch.float64, device=DEV)
+    before = _lib.launch_count()
+    check(lib.lob_dense_matmul(dt(X), B, N, N, C, ptr(A), N, N * N, ptr(X), ptr(Y), ptr(d), N, 1, ptr(dots), None, 0,
+                               stream(X)), "lob_dense_matmul")
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - before == 1  # one kernel, no split pass
+    ref = A.double() @ X.double() + d.double().unsqueeze(-1) * X.double()
+    assert ((Y.double() - ref).abs().max() / ref.abs().max()).item() < 3e-6 + 3.5e-9 * N
+    dref = (X.double() * ref).sum(-2)
+    assert ((dots.sum(1) - dref).abs().max() / dref.abs().max()).item() < 3e-6 + 3.5e-9 * N
