@@ -53,6 +53,32 @@ def test_argument_errors_come_back_through_the_abi():
     assert rc == -1
 
 
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    lib = _lib.load()
+    # lanczos: bad mode / iteration index / NULL pointers come back as argument errors, nothing is launched
+    assert lib.lob_lanczos_step(0, 5, 1, 8, 1, 4, 1, None, None, None, None, 1e-5, None) == -1
+    assert b"mode" in lib.lob_last_error()
+    assert lib.lob_lanczos_step(0, 0, 1, 8, 1, 4, 2, None, None, None, None, 1e-5, None) == -1  # mode 0 needs k = 0
+    assert lib.lob_lanczos_step(0, 1, 1, 8, 1, 4, 1, None, None, None, None, 1e-5, None) == -1
+    assert b"NULL" in lib.lob_last_error()
+    assert lib.lob_lanczos_init(0, 0, 8, 1, None, None, None) == -1
+    # streaming matmul scratch: (B, 2 * round_up(C, 8), K) floats for fp32, none for fp64 or C > 64
+    assert lib.lob_dense_matmul_workspace_bytes(0, 1024, 5000, 5000, 33) == 1024 * 80 * 5000 * 4
+    assert lib.lob_dense_matmul_workspace_bytes(1, 1024, 5000, 5000, 33) == 0
+    assert lib.lob_dense_matmul_workspace_bytes(0, 2, 100, 100, 65) == 0
+
+
+def test_lanczos_host_checks_and_no_cpu_fallback():
+    from linear_operator_b200.utils.lanczos import lanczos_tridiag
+
+    with pytest.raises(RuntimeError, match="matmul_closure should be a function callable object"):
+        lanczos_tridiag(torch.eye(3), 2, dtype=torch.float32, device="cpu", matrix_shape=(3, 3))
+    A = torch.eye(8)
+    with pytest.raises(_lib.LobError, match="CUDA tensors only"):
+        lanczos_tridiag(lambda v: A @ v, 4, dtype=torch.float32, device=torch.device("cpu"), matrix_shape=A.shape,
+                        init_vecs=torch.ones(8, 1))
+
+
 def test_no_cpu_fallback():
     op = DenseLinearOperator(torch.eye(8)).add_jitter(0.5)
     with settings.max_cholesky_size(0):
