@@ -395,3 +395,53 @@ def test_inv_quad_logdet_baseline_operator_size_vs_oracle():
     e_ld = np.abs(npy(ld) - ld_o) / np.abs(ld_o)
     print(f"N=5000 vs oracle: inv_quad rel err {e_iq.max():.2e}, logdet rel err {e_ld.max():.2e}")
     assert e_iq.max() < F32_RTOL and e_ld.max() < F32_RTOL
+
+
+@pytest.mark.parametrize("name,rt", [("entry_dense_f64", 1e-9), ("entry_dense_f32", F32_RTOL)])
+def test_solve_and_inv_quad_entry_points(golden, name, rt):
+    """SURVEY 8a row 17 against the reference's own outputs: op.solve (with and without left tensor, vector rhs on an
+    un-batched operator), torch.linalg.solve dispatch, op.inv_quad (reduced / not), default (loose) tolerance."""
+    g = golden(name)
+    A, d, rhs = cu(g["A"]), cu(g["d"]), cu(g["rhs"])
+    op = AddedDiagLinearOperator(DenseLinearOperator(A), DiagLinearOperator(d))
+    rank, tol = int(g["rank"]), float(g["tol"])
+    with settings.max_cholesky_size(0), settings.min_preconditioning_size(4), settings.max_preconditioner_size(rank), \
+            settings.cg_tolerance(tol), settings.max_cg_iterations(300):
+        sol = op.solve(rhs)
+        sol_l = op.solve(rhs, cu(g["lhs"]))
+        iq = op.inv_quad(rhs)
+        iq_nr = op.inv_quad(rhs, reduce_inv_quad=False)
+        sol_t = torch.linalg.solve(op, rhs)
+        op1 = AddedDiagLinearOperator(DenseLinearOperator(A[0]), DiagLinearOperator(d[0]))
+        sol_v = op1.solve(cu(g["vec"]))
+    with settings.max_cholesky_size(0), settings.min_preconditioning_size(4), settings.max_preconditioner_size(rank):
+        sol_def = op.solve(rhs)
+    assert sol.shape == g["solve"].shape and sol_l.shape == g["solve_left"].shape and sol_v.shape == g["solve_vec"].shape
+    assert iq.shape == g["inv_quad"].shape and iq_nr.shape == g["inv_quad_noreduce"].shape
+    assert relerr(npy(sol), g["solve"]) < rt
+    assert relerr(npy(sol_t), g["solve_torch"]) < rt
+    assert relerr(npy(sol_l), g["solve_left"]) < 10 * rt
+    assert relerr(npy(iq), g["inv_quad"]) < 10 * rt
+    assert relerr(npy(iq_nr), g["inv_quad_noreduce"]) < 10 * rt
+    assert relerr(npy(sol_v), g["solve_vec"]) < 10 * rt
+    assert relerr(npy(sol_def), g["solve_default"]) < 10 * rt
+
+
+def test_add_jitter_constant_diag_entry_points(golden):
+    """DenseLinearOperator.add_jitter -> AddedDiag(Dense, ConstantDiag) (stride-0 diagonal reaches the kernels):
+    inv_quad_logdet, logdet alone and solve against the reference's outputs."""
+    g = golden("entry_jitter_f64")
+    base = DenseLinearOperator(cu(g["A"])).add_jitter(float(g["jitter"]))
+    assert type(base).__name__ == "AddedDiagLinearOperator" and type(base._diag_tensor).__name__ == "ConstantDiagLinearOperator"
+    op = Injected(base._linear_op, base._diag_tensor)
+    op.probes = cu(g["probes"])
+    rhs = cu(g["rhs"])
+    with settings.max_cholesky_size(0), settings.min_preconditioning_size(4), settings.max_preconditioner_size(int(g["rank"])):
+        iq, ld = op.inv_quad_logdet(rhs, logdet=True)
+        ld_only = op.logdet()
+        with settings.cg_tolerance(1e-8), settings.max_cg_iterations(300):
+            sol = base.solve(rhs)
+    assert relerr(npy(iq), g["inv_quad"]) < 1e-9
+    assert relerr(npy(ld), g["logdet"]) < 1e-9
+    assert relerr(npy(ld_only), g["logdet_only"]) < 1e-9
+    assert relerr(npy(sol), g["solve"]) < 1e-8
