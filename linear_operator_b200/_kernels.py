@@ -488,11 +488,13 @@ def toeplitz_matmul(col: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor
         H = fx.shape[-1]
         fc_c = fc if fc_bs == 0 else fc[b0:b1]
         check(lib.lob_toeplitz_mul(dt(X), nb, C, H, ptr(fc_c), fc_bs, ptr(fx), stream(X)), "lob_toeplitz_mul")
-        yt = torch.fft.irfft(fx, n=L)  # cuFFT C2R (normalised by 1/L)
+        # cuFFT C2R, un-normalised (norm="forward" puts the 1/L on the forward transform, which we did not ask for):
+        # the 1/L goes into the un-padding kernel instead of a separate full pass over (B, C, L)
+        yt = torch.fft.irfft(fx, n=L, norm="forward")
         del fx
         dd_c = dd if (dd is None or d_bs == 0) else dd[b0:b1]
         check(
-            lib.lob_toeplitz_unpad(dt(X), nb, N, C, L, ptr(yt), 1.0, ptr(Xf[b0:b1]), ptr(dd_c), d_bs, d_st,
+            lib.lob_toeplitz_unpad(dt(X), nb, N, C, L, ptr(yt), 1.0 / L, ptr(Xf[b0:b1]), ptr(dd_c), d_bs, d_st,
                                    ptr(Y[b0:b1]), stream(X)),
             "lob_toeplitz_unpad",
         )

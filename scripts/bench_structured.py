@@ -68,7 +68,7 @@ if "kron" in which:
         print("[cfg3] FAILED:", type(e).__name__, e, flush=True)
 
 if "toeplitz" in which:
-    for B in (16, 64):
+    for B in ((16,) if "quick" in which else (16, 64)):
         try:
             torch.cuda.reset_peak_memory_stats()
             N = 2**20
