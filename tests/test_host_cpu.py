@@ -189,3 +189,29 @@ def test_preconditioner_gating_and_torch_function():
     with pytest.raises(NotImplementedError, match="next"):
         small._bilinear_derivative(None, None)
     assert lo.to_dense(torch.eye(2)).shape == (2, 2) and type(lo.to_linear_operator(torch.eye(2))) is DenseLinearOperator
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the oracle port timed on the host cores) keeps the driver's contract: exactly one JSON
+    line on stdout with the shared metric / config keys, impl = reference, a cpu_baseline and a zero-copy e2e object."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run(
+        [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+         "--cpu-sample-batch", "1", "--n", "300", "--batch", "4"],
+        capture_output=True, text=True, timeout=300, check=True,
+    ).stdout
+    lines = [ln for ln in out.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "calls/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
