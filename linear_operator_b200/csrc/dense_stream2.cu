@@ -304,17 +304,33 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           DS_LD16(taddr + c0, hi);
           DS_LD16(taddr + CP + c0, lo);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          double pd[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float y = fmaf(dv, e[i], (__uint_as_float(hi[i]) + __uint_as_float(lo[i])) * alpha_b);
-            if (rok && c0 + i < C) Yb[row * C + c0 + i] = y;
-            if (p.dots) {
-              // column sum of e * y over the 32 rows of this warp (fixed butterfly order: deterministic)
-              double pd = (rok && c0 + i < C) ? (double)e[i] * (double)y : 0.0;
+            const bool ok = rok && c0 + i < C;
+            if (ok) Yb[row * C + c0 + i] = y;
+            pd[i] = ok ? (double)e[i] * (double)y : 0.0;
+          }
+          if (p.dots) {
+            // Column sums of e * y over the 32 rows of this warp as a transpose-reduce: at each step a lane keeps half of
+            // its columns, ships the other half to its partner and adds what it receives -- 16 fp64 adds and 16 64-bit
+            // shuffles per chunk instead of 80 and 80 for sixteen independent butterflies (the fp64 pipe is what bounds
+            // the epilogue, ncu).  The summation tree is fixed: deterministic.
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) pd += __shfl_xor_sync(0xffffffffu, pd, o);
-              if (lane == i) red[(t * 4 + q) * 48 + c0 + i] = pd;
+            for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
+              const bool up = (lane & o) != 0;
+#pragma unroll
+              for (int j = 0; j < h; ++j) {
+                const double send = up ? pd[j] : pd[j + h];
+                const double keep = up ? pd[j + h] : pd[j];
+                pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              }
             }
+            pd[0] += __shfl_xor_sync(0xffffffffu, pd[0], 1);
+            // lane l now holds column 8 b4 + 4 b3 + 2 b2 + b1 of the chunk (b_k = bit k of l); lanes l and l^1 agree
+            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if ((lane & 1) == 0) red[(t * 4 + q) * 48 + c0 + col] = pd[0];
           }
         }
       }

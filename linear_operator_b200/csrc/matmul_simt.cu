@@ -326,10 +326,11 @@ static int dense_f32_tensor_paths(int64_t B, int64_t M, int64_t K, int64_t C, co
                                   cudaStream_t st) {
   const char* impl = getenv("LOB_DENSE_IMPL");
   if (getenv("LOB_DISABLE_TC") || (impl && !strcmp(impl, "simt"))) return LOB_ERR_UNSUPPORTED;
-  // Short contractions (the K = rank preconditioner product Q t) are per-tile-overhead bound in the persistent kernel
-  // (few k-blocks per 256-row tile, epilogue not hidden): they stay on the first-generation kernel unless pinned.
+  // dense_stream2 serves long contractions (streaming regime) and short ones (K <= 256: the preconditioner product
+  // Q t with the fused z, <r,z> epilogue -- 1.62 ms at config 2 since its epilogue reduces the fp64 partials with a
+  // transpose-reduce, against 2.25 ms for the first-generation kernel); the window in between stays on the older kernel.
   const bool pinned_stream2 = impl && !strcmp(impl, "stream2");
-  if (pinned_stream2 || (!impl && K >= 512)) {
+  if (pinned_stream2 || (!impl && (K >= 512 || (K <= 256 && a_bs != 0)))) {
     int s = dense_matmul_stream2_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, ws,
                                      ws_bytes, st);
     if (s != LOB_ERR_UNSUPPORTED) return s;
