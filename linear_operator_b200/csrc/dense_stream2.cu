@@ -16,7 +16,14 @@
 //     read per MMA (vs. 8 KB of A_lo + 4 KB of X in the first kernel), and the tensor time per k step drops from
 //     2 x 128 to 2 x (CP/2.67 + CP/5.3) cycles.
 //   D[:, c] = A_hi X_hi + A_lo X_hi,  D[:, CP + c] = A_hi X_lo:  y = D[:, c] + D[:, CP + c]   (3xTF32, fp32 accumulate)
-// TMEM (512 columns): 4 accumulators x 96 columns (2 M tiles x 2 buffers) + 128 columns of A_lo operand slots.
+// TMEM (512 columns): 4 accumulators x 2 CP columns (2 M tiles x 2 buffers: the epilogue of tile i overlaps the main
+// loop of tile i + 1) + the remaining columns as A_lo operand slots of 2 BK columns (3 slots at C = 33, BK = 32).
+// Warp roles (512 threads): 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 2-3 in-kernel X producers (only when no
+// workspace was supplied), 4-7 epilogue (thread = operator row: tcgen05.ld, hi + lo, alpha, + d (.) E, fp64 <E, Y>
+// partials by a transpose-reduce, direct stores), 8-15 converters.
+// Measured at BASELINE config 2 (B = 1024, N = 5000, C = 33): 19.9 - 21.7 ms per launch inside the power-capped solve
+// (0.74 - 0.81 of the measured HBM peak), DRAM traffic 1.025 x algorithmic, shared-memory data pipe 89.6 % busy (ncu,
+// profiles/r1_dense_stream2_ncu.md).
 #include <cuda.h>
 #include <stdlib.h>
 
