@@ -610,3 +610,99 @@ def lanczos_tridiag(matmul_closure, max_iter, init_vecs, tol=1e-5):
     if c == 1:
         q, t = q[0], t[0]
     return q, t
+
+
+# ------------------------------------------------------------------------------------------------
+# Backward pass of inv_quad_logdet for AddedDiag(Dense(A), Diag(d))   (SURVEY 8f rank 1 -- oracle only so far)
+#   InvQuadLogdet.backward            functions/_inv_quad_logdet.py:163-226
+#   _bilinear_derivative              operators/_linear_operator.py:336-393 (autograd of sum(left * (K right)))
+#   PivotedCholesky.backward          functions/_pivoted_cholesky.py:106-150
+#   d logdet_P / d(L, d)              autograd through the QR of added_diag_linear_operator.py:144-184
+# ------------------------------------------------------------------------------------------------
+def _cholesky_backward(C, gC):
+    """Gradient of A -> chol(A) (lower) for a symmetric A, given the gradient w.r.t. the factor: the formula autograd
+    uses, C^-T Phi(C^T gC) C^-1 with Phi = tril with a halved diagonal, symmetrised."""
+    P = np.tril(np.swapaxes(C, -1, -2) @ gC)
+    idx = np.arange(C.shape[-1])
+    P[..., idx, idx] *= 0.5
+    Cinv = np.linalg.inv(C)
+    S = np.swapaxes(Cinv, -1, -2) @ P @ Cinv
+    return 0.5 * (S + np.swapaxes(S, -1, -2))
+
+
+def pivoted_cholesky_backward(A, perm, m, grad_L):
+    """Gradient w.r.t. the dense operator ``A (*b, N, N)`` of its rank-m pivoted Cholesky factor ``L (*b, N, m)``
+    (functions/_pivoted_cholesky.py:106-150: L is recomputed as K[pi, pi[:m]] chol(K[pi[:m], pi[:m]])^-T, rows permuted
+    back, and differentiated by autograd; restated with the explicit Cholesky / triangular-solve adjoints)."""
+    *batch_shape, n, _ = A.shape
+    gA = np.zeros_like(A)
+    for b in np.ndindex(*batch_shape):
+        pi = perm[b]
+        short = pi[:m]
+        Kpm = A[b][np.ix_(pi, short)]                    # apply_permutation(matrix, full, short)   (:125)
+        C = np.linalg.cholesky(Kpm[:m])                  # psd_safe_cholesky(Krows[:m])             (:128)
+        Lp = np.concatenate([C, np.linalg.solve(C, Kpm[m:].T).T], axis=0)  # res_pivoted            (:131-137)
+        G = grad_L[b][pi]                                # gradient in pivoted row order
+        # rows m..N-1:  Lp2 = K2 C^-T   ->  gK2 = G2 C^-1,  gC += -(C^-1 G2^T Lp2)^T restricted to the lower triangle
+        Cinv = np.linalg.inv(C)
+        G2, L2 = G[m:], Lp[m:]
+        gK2 = G2 @ Cinv
+        gC = G[:m].copy()
+        gC -= np.tril(Cinv.T @ (G2.T @ L2))
+        gKmm = _cholesky_backward(C, np.tril(gC))
+        gKpm = np.concatenate([gKmm, gK2], axis=0)
+        np.add.at(gA[b], np.ix_(pi, short), gKpm)        # indexing backward: scatter-add
+    return gA
+
+
+def dense_added_diag_inv_quad_logdet_backward(A, d, rhs, probes, grad_inv_quad, grad_logdet, precond_rank=None,
+                                              min_precond_size=None, precond_tol=None, **cg_kwargs):
+    """Gradients ``(grad_A, grad_d, grad_rhs)`` of ``sum_b grad_inv_quad_b * inv_quad_b + grad_logdet_b * logdet_b`` as
+    the reference's backward computes them (NOT the exact derivative of the stochastic forward estimate: the probe
+    solves stand in for K^-1, functions/_inv_quad_logdet.py:178-215).  ``probes`` are injected, column-normalised
+    (norms = 1); ``grad_inv_quad`` is per batch element (reduce_inv_quad=True upstream)."""
+    n = A.shape[-1]
+    s = probes.shape[-1]
+    if precond_rank is None:
+        precond_rank = DEFAULTS["max_preconditioner_size"]
+    if min_precond_size is None:
+        min_precond_size = DEFAULTS["min_preconditioning_size"]
+    matmul = lambda v: dense_added_diag_matmul(A, d, v)  # noqa: E731
+    closure, logdet_p, L, perm = None, 0.0, None, None
+    if precond_rank > 0 and n >= min_precond_size:
+        batch_shape = A.shape[:-2]
+
+        def get_rows(pi):
+            Ab = np.broadcast_to(A, batch_shape + A.shape[-2:])
+            return np.take_along_axis(Ab, pi[..., None, None].repeat(n, axis=-1), axis=-2)[..., 0, :]
+
+        L, perm = pivoted_cholesky(np.diagonal(A, axis1=-1, axis2=-2), get_rows, precond_rank, precond_tol)
+        closure, logdet_p, _ = added_diag_preconditioner(L, d)
+    _, _, solves = inv_quad_logdet(matmul, n, rhs, probes, closure, logdet_p, **cg_kwargs)
+
+    g_ld = np.asarray(grad_logdet)[..., None, None]
+    g_iq = np.asarray(grad_inv_quad)[..., None, None]          # the same weight for every rhs column (reduced sum)
+    coef = 1.0 / s                                             # :181
+    probe_solves = solves[..., :s] * coef * g_ld               # :182-183 (norms = 1)
+    ppv = closure(probes) if closure is not None else probes   # :187-190
+    iq_solves = solves[..., s:]                                # :199
+    neg = -iq_solves * g_iq                                    # :200
+    left = np.concatenate([probe_solves, neg], axis=-1)        # :204
+    right = np.concatenate([ppv, iq_solves], axis=-1)          # :205
+    grad_A = left @ np.swapaxes(right, -1, -2)                 # _bilinear_derivative of the dense part
+    grad_d = (left * right).sum(-1)                            # ... and of the diagonal part
+    grad_rhs = -2.0 * neg                                      # :214
+    if L is not None:
+        # precond_lt = L L^T + D:  _bilinear_derivative(-ppv * coef, ppv * g_ld)   (:209-211)
+        u, v = -ppv * coef, ppv * g_ld
+        Lt = np.swapaxes(L, -1, -2)
+        grad_L = u @ np.swapaxes(Lt @ v, -1, -2) + v @ np.swapaxes(Lt @ u, -1, -2)
+        grad_d = grad_d + (u * v).sum(-1)
+        # logdet_P = log det(L L^T + D) is added to the estimate (operators/_linear_operator.py:1801) and sits in the
+        # autograd graph through the QR of added_diag_linear_operator.py:164/:176
+        P = L @ Lt + d[..., None] * np.eye(n, dtype=A.dtype)
+        Pinv = np.linalg.inv(P)
+        grad_L = grad_L + np.asarray(grad_logdet)[..., None, None] * 2.0 * (Pinv @ L)
+        grad_d = grad_d + np.asarray(grad_logdet)[..., None] * np.diagonal(Pinv, axis1=-1, axis2=-2)
+        grad_A = grad_A + pivoted_cholesky_backward(A, perm, L.shape[-1], grad_L)
+    return grad_A, grad_d, grad_rhs
