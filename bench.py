@@ -11,8 +11,13 @@ sc = logspace(0,-1.5,256).
 
 Prints ONE JSON line (rank 0).  `value` = calls/s with the operator resident in HBM; `e2e` = the same call fed from
 pinned HOST memory (H2D of the operator + rhs and D2H of the results inside the timed region); `roofline` is for the
-dominant kernel (the dense operator matmul); `cpu_baseline` is the numpy oracle port of the reference
-timed on the host cores on a bounded batch slice.
+dominant kernel (the dense operator matmul); `cpu_baseline` is the reference itself (the unmodified
+package installed into the git-ignored baseline/_ref, `kind: "reference"`; the numpy oracle port, `kind: "port"`, only
+when that install is absent) timed on the host cores on a bounded batch slice.
+
+`--impl reference`     the same CPU arm as its own JSON line (rank 0 only under torchrun).
+`--impl reference-gpu` (not part of the driver contract) the unmodified reference with its tensors on cuda:0 -- the
+                       north star's denominator; output kept under profiles/.
 """
 from __future__ import annotations
 
@@ -37,7 +42,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--batch", type=int, default=CFG["B"], help="per-GPU batch (default: the BASELINE config)")
     ap.add_argument("--n", type=int, default=CFG["N"])
     ap.add_argument("--cpu-sample-batch", type=int, default=16)
@@ -72,26 +77,94 @@ def cpu_step(inp):
                                                precond_rank=CFG["rank"], min_precond_size=2000)
 
 
+def load_reference():
+    """The unmodified reference package from baseline/_ref (pip --target install of /root/reference, DESIGN.md
+    section 8), or None when it is not there."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "linear_operator")):
+        return None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import linear_operator as ref  # noqa: F401
+
+        return ref
+    except Exception as exc:  # missing dependency on this box: fall back to the port, say why
+        sys.stderr.write(f"bench.py: reference import failed ({exc!r}); using the oracle port\n")
+        return None
+
+
+def host_threads():
+    """Threads the CPU arm really uses: torch.distributed.run exports OMP_NUM_THREADS=1 for its workers, so ask for
+    all cores explicitly and report what torch grants."""
+    import torch
+
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def reference_step_fn(ref, device):
+    """One cold inv_quad_logdet of the unmodified reference on `device` (its public API, stock code path)."""
+    import torch
+
+    Dense = ref.operators.DenseLinearOperator
+    Diag = ref.operators.DiagLinearOperator
+    Added = ref.operators.AddedDiagLinearOperator
+
+    def step(K, d, rhs):
+        with ref.settings.num_trace_samples(CFG["S"]), ref.settings.max_preconditioner_size(CFG["rank"]), \
+                torch.no_grad():
+            op = Added(Dense(K), Diag(d))
+            return op.inv_quad_logdet(rhs, logdet=True)
+
+    return step
+
+
 def time_cpu(bs, n, steps, warmup):
-    inp = cpu_inputs(bs, n)
+    """-> (seconds per step on the batch slice, kind, threads)"""
+    import torch
+
+    threads = host_threads()
+    ref = load_reference()
+    K, d, rhs, eps_root, eps_diag = cpu_inputs(bs, n)
+    if ref is not None:
+        kind = "reference"
+        step = reference_step_fn(ref, "cpu")
+        Kt, dt_, rt = torch.from_numpy(K), torch.from_numpy(d), torch.from_numpy(rhs)
+        run = lambda: step(Kt, dt_, rt)  # noqa: E731
+    else:
+        kind = "port"
+        inp = (K, d, rhs, eps_root, eps_diag)
+        run = lambda: cpu_step(inp)  # noqa: E731
+    torch.manual_seed(0)
     for _ in range(warmup):
-        cpu_step(inp)
+        run()
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_step(inp)
-    dt_step = (time.perf_counter() - t0) / steps
-    return dt_step
+        run()
+    return (time.perf_counter() - t0) / steps, kind, threads
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     bs = args.cpu_sample_batch
-    dt_step = time_cpu(bs, args.n, args.steps, args.warmup)
-    calls_per_s = (bs / args.batch) / dt_step  # batch elements are independent: scale the slice to the full batch
-    cores = os.cpu_count()
-    sample = f"batch slice {bs} of {args.batch} (N={args.n}, same generator), scaled linearly to the full batch"
+    dt_step, kind, threads = time_cpu(bs, args.n, args.steps, args.warmup)
+    # the repo arm scales weakly: `world` GPUs hold world * batch problems.  Batch elements are independent, so the
+    # slice is scaled linearly to that global batch.
+    global_batch = args.batch * world
+    calls_per_s = (bs / global_batch) / dt_step
+    sample = (f"batch slice {bs} of {global_batch} (N={args.n}, same generator), {args.warmup} warm-up + {args.steps} "
+              f"timed cold calls, scaled linearly to the global batch")
+    what = ("the unmodified reference (baseline/_ref, torch CPU tensors)" if kind == "reference"
+            else "numpy oracle port of the reference's CPU path (baseline/_ref is absent on this box)")
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -100,19 +173,67 @@ def run_reference(args):
         "n_gpus": args.gpus,
         "steps": args.steps,
         "warmup": args.warmup,
-        "ms_per_step": dt_step * 1e3 * (args.batch / bs),
+        "ms_per_step": dt_step * 1e3 * (global_batch / bs),
+        "sample_ms_per_step": dt_step * 1e3,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": calls_per_s, "unit": "calls/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": calls_per_s, "unit": "calls/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": calls_per_s, "unit": "calls/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "numpy oracle port of the reference's CPU path (the reference is pure Python/PyTorch and does not "
-                "travel to the GPU box); all host threads through the BLAS",
+        "note": f"{what}; {threads} host threads (torch.set_num_threads, overriding torchrun's OMP_NUM_THREADS=1)",
     }
     emit(line)
+
+
+def run_reference_gpu(args):
+    """North-star denominator: the UNMODIFIED reference with its tensors on cuda:0, same workload, cold calls,
+    CUDA-event timed.  Not a driver arm; run by hand under gpurun and kept in profiles/."""
+    import torch
+
+    ref = load_reference()
+    if ref is None:
+        emit({"impl": "reference-gpu", "unavailable": "baseline/_ref is absent"})
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, N = args.batch, args.n
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    sc = torch.logspace(0, -1.5, CFG["wrank"], device=dev)
+    sc = sc / sc.norm()
+    K = torch.empty(B, N, N, device=dev)
+    for s0 in range(0, B, 32):
+        e0 = min(s0 + 32, B)
+        W = torch.randn(e0 - s0, N, CFG["wrank"], device=dev, generator=gen) * sc
+        torch.bmm(W, W.mT, out=K[s0:e0])
+    del W
+    d = torch.full((B, N), CFG["diag"], device=dev)
+    rhs = torch.randn(B, N, 1, device=dev, generator=gen)
+    step = reference_step_fn(ref, dev)
+    sampler = ClockSampler(0)
+    torch.manual_seed(4321)
+    for _ in range(args.warmup):
+        iq, ld = step(K, d, rhs)
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        iq, ld = step(K, d, rhs)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    emit({
+        "impl": "reference-gpu", "metric": METRIC, "value": 1e3 / ms, "unit": "calls/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, 1), "clocks": sampler.stop(),
+        "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+        "result_check": {"inv_quad_mean": float(iq.mean()), "logdet_mean": float(ld.mean())},
+        "note": "unmodified cornellius-gp/linear_operator (baseline/_ref), tensors on cuda:0, stock code path "
+                "(torch.matmul -> cuBLAS, ATen elementwise, cuSOLVER QR, CPU LAPACK eigh of the tridiagonals)",
+    })
 
 
 def workload_config(args, world):
@@ -264,6 +385,31 @@ def run_ours(args):
     ms_per_step = elapsed_ms / args.steps
     value = world * 1e3 / ms_per_step
 
+    # ---- strong scaling (SURVEY 8e's partition): ONE global batch of `B` problems split by shard_bounds, every rank
+    # runs its slice, one all_gather of the results inside the timed region ----
+    strong = {"global_batch": B, "value": value, "unit": "calls/s", "ms_per_step": ms_per_step,
+              "per_gpu_batch": B, "note": "identical to `value` at 1 GPU"}
+    if world > 1:
+        from linear_operator_b200.distributed import shard_bounds
+
+        s0, s1 = shard_bounds(B, rank, world)
+        for _ in range(2):
+            iq_s, ld_s = step(K[s0:s1], d[s0:s1], rhs[s0:s1])
+            gather_results(iq_s, ld_s, B)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            iq_s, ld_s = step(K[s0:s1], d[s0:s1], rhs[s0:s1])
+            gather_results(iq_s, ld_s, B)
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_strong = float(t.item()) / args.steps
+        strong = {"global_batch": B, "value": 1e3 / ms_strong, "unit": "calls/s", "ms_per_step": ms_strong,
+                  "per_gpu_batch": s1 - s0,
+                  "note": "fixed global batch split over the ranks (strong scaling), all_gather inside the timed region"}
+
     # ---- end to end: operator + rhs start in pinned HOST memory every step, results read back ----
     e2e = None
     if not args.no_e2e:
@@ -302,10 +448,11 @@ def run_ours(args):
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         bs = args.cpu_sample_batch
-        dt_step = time_cpu(bs, N, 1, 1)
-        cpu_base = {"value": (bs / B) / dt_step, "unit": "calls/s", "cores": os.cpu_count(), "kind": "port",
-                    "sample": f"batch slice {bs} of {B} (N={N}), 1 warm-up + 1 timed call of the numpy oracle, scaled "
-                              "linearly to the full batch"}
+        dt_step, kind, threads = time_cpu(bs, N, 2, 1)
+        cpu_base = {"value": (bs / B) / dt_step, "unit": "calls/s", "cores": threads, "kind": kind,
+                    "sample": f"batch slice {bs} of {B} (N={N}), 1 warm-up + 2 timed cold calls of "
+                              + ("the unmodified reference on torch CPU tensors" if kind == "reference"
+                                 else "the numpy oracle port") + ", scaled linearly to the full batch"}
 
     if rank == 0:
         line = {
@@ -313,7 +460,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "cg_iters_per_s": value * 21, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
-            "roofline": roof, "cpu_baseline": cpu_base,
+            "roofline": roof, "cpu_baseline": cpu_base, "strong_scaling": strong,
             "result_check": {"inv_quad_mean": float(iq_all.mean()), "logdet_mean": float(ld_all.mean()),
                              "gathered": int(iq_all.numel())},
         }
@@ -431,6 +578,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_ours(args)
 

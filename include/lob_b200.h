@@ -157,6 +157,25 @@ int lob_pivchol_kron(int32_t dtype, int64_t B, int32_t n_factors, const int64_t*
 int lob_pivchol_toeplitz(int32_t dtype, int64_t B, int64_t N, const void* col, int64_t col_batch_stride, int32_t rank,
                          double error_tol, void* Lt, int64_t* perm, int32_t* m_out, void* ws, void* stream);
 
+/* Generic operators (RootLinearOperator, SumLinearOperator, user-defined classes): the same pivoted Cholesky with the
+ * pivot row of every step supplied by the caller, who evaluates the operator's own `_get_indices`
+ * (operators/_linear_operator.py:412-461 through utils/permutation.py:76-87) on the device-resident pivot indices:
+ *   lob_pivchol_rows_begin (diag (B,N) = operator._approx_diagonal(), _pivoted_cholesky.py:26-31)
+ *   for m in 0..rank-1:  lob_pivchol_rows_pivot  -> pivot_rows (B) int64 = pi_m (:61-70), sqrt on the diagonal (:73-74)
+ *                        rows (B,N) = op[b, pi_m[b], :]                         (host: `_get_indices`, :79)
+ *                        lob_pivchol_rows_update                                (:80-98)
+ *   lob_pivchol_rows_status -> m_out = steps taken, active_out = loop still running (optional early-exit poll)
+ * Lt (B, rank, N) zero-filled on entry, perm (B, N) int64, ws = lob_pivchol_workspace_bytes(); the stop rule (:57)
+ * lives on the device: after it fires, pivot/update launches are no-ops. */
+int lob_pivchol_rows_begin(int32_t dtype, int64_t B, int64_t N, int32_t rank, const void* diag, int64_t* perm,
+                           void* ws, void* stream);
+int lob_pivchol_rows_pivot(int32_t dtype, int64_t B, int64_t N, int32_t rank, int32_t m, double error_tol, void* Lt,
+                           int64_t* perm, int64_t* pivot_rows, void* ws, void* stream);
+int lob_pivchol_rows_update(int32_t dtype, int64_t B, int64_t N, int32_t rank, int32_t m, const void* rows, void* Lt,
+                            void* ws, void* stream);
+int lob_pivchol_rows_status(int32_t dtype, int64_t B, int64_t N, int32_t rank, int32_t* m_out, int32_t* active_out,
+                            void* ws, void* stream);
+
 /* (B, R, N) -> (B, N, m) keeping the first m rows: the `L[..., :m, :].mT.contiguous()` of _pivoted_cholesky.py:104 */
 int lob_transpose_rows(int32_t dtype, int64_t B, int64_t R, int64_t N, int64_t m, const void* Lt, void* L,
                        void* stream);

@@ -12,7 +12,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import check, dt, ptr, require_cuda, stream, workspace
+from ._lib import check, device_guard, dt, ptr, require_cuda, stream, workspace
 
 
 # bench.py sets this to a list to collect (start, end) CUDA events around every dense operator matmul launch, recorded
@@ -262,6 +262,54 @@ def pivoted_cholesky_toeplitz(col: torch.Tensor, rank: int, tol: float):
     return _pivchol_finish(lib, Lt, perm, m_out, batch_shape, N, rankmax)
 
 
+def pivoted_cholesky_rows(op, rank: int, tol: float, poll_every: int = 8):
+    """Pivoted Cholesky of ANY operator that implements ``_get_indices`` and ``_approx_diagonal`` (Root, Sum, user
+    classes): the reference's generic route (functions/_pivoted_cholesky.py:57-98 -> utils/permutation.py:76-87 ->
+    ``LinearOperator._get_indices``), with the pivot search / row update / stop rule in the same device kernels as the
+    dense case.  The pivot indices stay on the device; the host polls the stop flag every ``poll_every`` steps only to
+    skip useless row fetches after an early stop."""
+    lib = _lib.load()
+    batch_shape = op.batch_shape
+    N = op.size(-1)
+    B = _numel(batch_shape)
+    diag = op._approx_diagonal()
+    require_cuda(diag)
+    dev, dty = diag.device, diag.dtype
+    diag = diag.expand(*batch_shape, N).reshape(B, N).contiguous()
+    rankmax = min(int(rank), N)
+    Lt = torch.zeros(B, rankmax, N, dtype=dty, device=dev)
+    perm = torch.empty(B, N, dtype=torch.int64, device=dev)
+    pi = torch.zeros(B, dtype=torch.int64, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    ws = workspace(lib.lob_pivchol_workspace_bytes(B, N, rankmax), dev)
+    st = stream(diag)
+    check(lib.lob_pivchol_rows_begin(dt(diag), B, N, rankmax, ptr(diag), ptr(perm), ptr(ws), st), "lob_pivchol_rows_begin")
+    # index tensors of the row gather  op[(*batch_indices, pi_m, arange(N))]  (utils/permutation.py:66-87)
+    cols = torch.arange(N, device=dev).expand(*batch_shape, N)
+    batch_idx = []
+    for i, sz in enumerate(batch_shape):
+        shape = [1] * (len(batch_shape) + 1)
+        shape[i] = sz
+        batch_idx.append(torch.arange(sz, device=dev).reshape(shape).expand(*batch_shape, N))
+    for m in range(rankmax):
+        check(lib.lob_pivchol_rows_pivot(dt(diag), B, N, rankmax, m, float(tol), ptr(Lt), ptr(perm), ptr(pi), ptr(ws), st),
+              "lob_pivchol_rows_pivot")
+        if m + 1 < N:
+            rows_idx = pi.reshape(*batch_shape, 1).expand(*batch_shape, N)
+            row = op._get_indices(rows_idx, cols, *batch_idx)
+            row = row.to(dty).expand(*batch_shape, N).reshape(B, N).contiguous()
+            check(lib.lob_pivchol_rows_update(dt(diag), B, N, rankmax, m, ptr(row), ptr(Lt), ptr(ws), st),
+                  "lob_pivchol_rows_update")
+        if poll_every and (m + 1) % poll_every == 0 and m + 1 < rankmax:
+            check(lib.lob_pivchol_rows_status(dt(diag), B, N, rankmax, ptr(status), ptr(status[1:]), ptr(ws), st),
+                  "lob_pivchol_rows_status")
+            if int(status[1].item()) == 0:
+                break
+    check(lib.lob_pivchol_rows_status(dt(diag), B, N, rankmax, ptr(status), ptr(status[1:]), ptr(ws), st),
+          "lob_pivchol_rows_status")
+    return _pivchol_finish(lib, Lt, perm, status[:1], batch_shape, N, rankmax)
+
+
 class AddedDiagPreconditioner:
     """M = L L^T + D from a pivoted-Cholesky factor (added_diag_linear_operator.py:144-184).
 
@@ -305,7 +353,7 @@ class AddedDiagPreconditioner:
             self._alpha = torch.full((B,), -1.0, dtype=dty, device=dev)  # z = r/d - w
             self._dscale = self.noise.reciprocal()  # (B, N)
         self.logdet = self.logdet.reshape(self.batch_shape) if len(self.batch_shape) else self.logdet.squeeze()
-        self._info = info
+        self.info = info  # (B,) int32, != 0: non-positive pivot in the k x k factorisation
 
     def _apply(self, v: torch.Tensor, want_dots: bool):
         require_cuda(v)
@@ -380,13 +428,23 @@ def col_dots(U: torch.Tensor, u_off: int, V: torch.Tensor, v_off: int, R: int) -
 
 
 def tridiag_eigh_slq(t_mat: torch.Tensor, n: int, want_evals=False, want_evecs=False, want_logdet=True):
-    """t_mat (S, *b, T, T).  Returns dict with the requested of evals (S,*b,T), evecs (S,*b,T,T), logdet (*b)."""
+    """t_mat (*lead, T, T) symmetric tridiagonal.  evals (*lead, T) / evecs (*lead, T, T) accept any leading shape like
+    the reference's eigh-based version (utils/lanczos.py:167-189; ``lanczos_tridiag`` squeezes the probe dimension for a
+    single vector, so a bare (T, T) matrix arrives here too).  The quadrature ``logdet`` (*b) needs the
+    (S, *b, T, T) layout: it sums over the leading probe dimension."""
     require_cuda(t_mat)
     lib = _lib.load()
-    S = t_mat.shape[0]
-    batch_shape = t_mat.shape[1:-2]
+    if t_mat.dim() < 2 or t_mat.shape[-1] != t_mat.shape[-2]:
+        raise RuntimeError(f"expected (*, T, T) tridiagonal matrices, got {tuple(t_mat.shape)}")
+    if want_logdet and t_mat.dim() < 3:
+        raise RuntimeError("the quadrature needs t_mat of shape (num_probes, *batch, T, T)")
+    lead = t_mat.shape[:-2]
     T = t_mat.shape[-1]
-    B = _numel(batch_shape)
+    if want_logdet:
+        S, batch_shape = int(lead[0]), lead[1:]
+        B = _numel(batch_shape)
+    else:  # eigendecomposition only: every matrix is its own problem
+        S, batch_shape, B = _numel(lead), lead, 1
     tf = t_mat.contiguous()
     dev, dty = t_mat.device, t_mat.dtype
     evals = torch.empty(S, B, T, dtype=dty, device=dev) if want_evals else None
@@ -401,9 +459,9 @@ def tridiag_eigh_slq(t_mat: torch.Tensor, n: int, want_evals=False, want_evecs=F
     )
     out = {}
     if want_evals:
-        out["evals"] = evals.reshape(S, *batch_shape, T)
+        out["evals"] = evals.reshape(*lead, T)
     if want_evecs:
-        out["evecs"] = evecs.reshape(S, *batch_shape, T, T)
+        out["evecs"] = evecs.reshape(*lead, T, T)
     if want_logdet:
         out["logdet"] = logdet.reshape(batch_shape)
     return out
@@ -471,7 +529,13 @@ def toeplitz_matmul(col: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor
     if fc_cache is None:
         fc_cache = toeplitz_embed_fft(col)
     fc, L = fc_cache
-    fc_bs = 0 if fc.shape[0] == 1 and B > 1 else fc.shape[-1]
+    if fc.shape[0] == 1:
+        fc_bs = 0
+    elif fc.shape[0] == B:
+        fc_bs = fc.shape[-1]
+    else:  # the column's batch is a proper sub-batch of the broadcast batch: materialise the broadcast spectrum
+        fc = fc.reshape(*col.shape[:-1], fc.shape[-1]).expand(*batch_shape, fc.shape[-1]).reshape(B, -1).contiguous()
+        fc_bs = fc.shape[-1]
     Y = torch.empty(B, N, C, dtype=X.dtype, device=X.device)
     dd, d_bs, d_st = _diag_args(d, batch_shape, N)
     # The padded transposes and the spectrum are 3 x (B, C, L) scratch: at BASELINE config 4 (B = 64, N = 2^20, 33
@@ -544,3 +608,13 @@ def lanczos_step(mode: int, k: int, w: Optional[torch.Tensor], q_mat: torch.Tens
                              stream(q_mat)),
         "lob_lanczos_step",
     )
+
+
+# Every launch goes to the current stream of the tensors' own device; make that device current for the duration of the
+# call when the caller's current device is another one (multi-GPU processes).
+for _name, _obj in list(globals().items()):
+    if callable(_obj) and getattr(_obj, "__module__", None) == __name__ and not _name.startswith("_") \
+            and not isinstance(_obj, type):
+        globals()[_name] = device_guard(_obj)
+AddedDiagPreconditioner.__init__ = device_guard(AddedDiagPreconditioner.__init__)
+AddedDiagPreconditioner._apply = device_guard(AddedDiagPreconditioner._apply)

@@ -107,6 +107,10 @@ _SIGS = {
         ctypes.c_int,
         [c_int32, c_int64, c_int64, _P, c_int64, c_int32, c_double, _P, _P, _P, _P, _P],
     ),
+    "lob_pivchol_rows_begin": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int32, _P, _P, _P, _P]),
+    "lob_pivchol_rows_pivot": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int32, c_int32, c_double, _P, _P, _P, _P, _P]),
+    "lob_pivchol_rows_update": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
+    "lob_pivchol_rows_status": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int32, _P, _P, _P, _P]),
     "lob_transpose_rows": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, c_int64, _P, _P, _P]),
     "lob_precond_factor": (
         ctypes.c_int,
@@ -191,6 +195,38 @@ def require_cuda(*tensors):
                 "linear_operator_b200 computes on CUDA tensors only (sm_100a kernels, no CPU fallback); "
                 f"got a tensor on {t.device}."
             )
+
+
+def _first_cuda_device(objs):
+    for o in objs:
+        if torch.is_tensor(o):
+            if o.is_cuda:
+                return o.device
+        elif isinstance(o, (list, tuple)):
+            d = _first_cuda_device(o)
+            if d is not None:
+                return d
+        elif hasattr(o, "representation") and callable(o.representation):  # a LinearOperator
+            d = _first_cuda_device(o.representation())
+            if d is not None:
+                return d
+    return None
+
+
+def device_guard(fn):
+    """Runs ``fn`` with the device of its first CUDA tensor argument as the current device: the C ABI launches on the
+    stream handle it is given, which belongs to that device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = _first_cuda_device(args) or _first_cuda_device(tuple(kwargs.values()))
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapped
 
 
 def ptr(t) -> c_void_p:

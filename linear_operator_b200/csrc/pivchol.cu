@@ -96,6 +96,14 @@ struct ToeplitzSrc {  // toeplitz_linear_operator.py:38-40, :25-31
   }
 };
 
+template <typename T>
+struct RowBufSrc {  // generic operators: the host fetched the pivot row (or the diagonal) through `_get_indices`
+  const T* buf;     // (B, n): entry(b, r, i) = buf[b, i] whatever r is -- the caller guarantees buf holds row r = pi[b]
+  int64_t n;
+  __device__ __forceinline__ T diag(int64_t b, int64_t i) const { return buf[b * n + i]; }
+  __device__ __forceinline__ T entry(int64_t b, int64_t, int64_t i) const { return buf[b * n + i]; }
+};
+
 // candidate ordering: NaN beats everything (torch.max propagates NaN), then larger value, then smaller position
 template <typename T>
 __device__ __forceinline__ bool cand_better(T v1, int p1, T v2, int p2) {
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(1024)
 k_pc_pivot(int64_t B, int64_t N, int rankmax, int m, int nchunks, double tol, const T* __restrict__ cval,
            const int* __restrict__ cpos, const int* __restrict__ cidx, const double* __restrict__ errsum,
            T* __restrict__ orig, int* __restrict__ pos, int64_t* __restrict__ perm, int* __restrict__ pi,
-           T* __restrict__ piv, T* __restrict__ Lt, PcControl* ctrl) {
+           T* __restrict__ piv, T* __restrict__ Lt, PcControl* ctrl, int64_t* __restrict__ pi64 = nullptr) {
   __shared__ int any_gt, any_nan;
   if (!ctrl->active) return;
   if (threadIdx.x == 0) {
@@ -233,6 +241,7 @@ k_pc_pivot(int64_t B, int64_t N, int rankmax, int m, int nchunks, double tol, co
     if (bp != m) pos[b * N + old] = bp;
     const T root = (T)sqrt((double)bv);
     pi[b] = bi;
+    if (pi64) pi64[b] = bi;
     piv[b] = root;
     Lt[(b * rankmax + m) * N + bi] = root;  // :73-74
   }
@@ -312,6 +321,10 @@ k_pc_update(Src src, int64_t N, int rankmax, int m, int nchunks, int64_t cpc, T*
 }
 
 __global__ void k_pc_finish(const PcControl* ctrl, int32_t* m_out) { *m_out = ctrl->m; }
+__global__ void k_pc_status(const PcControl* ctrl, int32_t* m_out, int32_t* active_out) {
+  *m_out = ctrl->m;
+  if (active_out) *active_out = ctrl->active;
+}
 
 template <typename T, typename Src>
 static int run_pivchol(Src src, int64_t B, int64_t N, int rank, double tol, T* Lt, int64_t* perm, int32_t* m_out,
@@ -406,5 +419,89 @@ extern "C" int lob_pivchol_toeplitz(int32_t dtype, int64_t B, int64_t N, const v
   LOB_DISPATCH_DTYPE(dtype, {
     ToeplitzSrc<scalar_t> src{(const scalar_t*)col, col_batch_stride};
     return run_pivchol<scalar_t>(src, B, N, rank, error_tol, (scalar_t*)Lt, perm, m_out, ws, (cudaStream_t)stream);
+  });
+}
+
+// ---- generic operators: the pivot row of every step comes from the operator's own `_get_indices`, called by the host
+// with the device-resident pivot indices (functions/_pivoted_cholesky.py:57-98 + utils/permutation.py:9-88).  Same
+// kernels, same index semantics; no host read per step (the indices never leave the device).
+namespace lob {
+template <typename T>
+static int pc_rows_step(int phase, int64_t B, int64_t N, int rank, int m, double tol, const T* buf, T* Lt,
+                        int64_t* perm, int64_t* pi64, int32_t* m_out, int32_t* active_out, void* ws, cudaStream_t st) {
+  LOB_REQUIRE(B > 0 && N > 0 && rank > 0, "lob_pivchol_rows: sizes must be positive");
+  LOB_REQUIRE(B <= 65535, "lob_pivchol_rows: flattened batch > 65535 not supported");
+  LOB_REQUIRE(N < (1LL << 31), "lob_pivchol_rows: N must fit in int32");
+  LOB_REQUIRE(ws != nullptr, "lob_pivchol_rows: NULL workspace");
+  const int rankmax = (int)(rank < N ? rank : N);
+  PcLayout L = pc_layout(B, N, rankmax, sizeof(T));
+  char* w = (char*)ws;
+  PcControl* ctrl = (PcControl*)(w + L.off_ctrl);
+  T* diag = (T*)(w + L.off_diag);
+  int* pos = (int*)(w + L.off_pos);
+  T* cval = (T*)(w + L.off_cand_val);
+  int* cpos = (int*)(w + L.off_cand_pos);
+  int* cidx = (int*)(w + L.off_cand_idx);
+  double* errsum = (double*)(w + L.off_errsum);
+  int* pi = (int*)(w + L.off_pi);
+  T* piv = (T*)(w + L.off_piv);
+  T* orig = (T*)(w + L.off_orig);
+  dim3 grid((unsigned)L.nchunks, (unsigned)B);
+  RowBufSrc<T> src{buf, N};
+  switch (phase) {
+    case 0:
+      LOB_REQUIRE(buf && perm, "lob_pivchol_rows_begin: NULL pointer");
+      k_pc_init<T, RowBufSrc<T>><<<grid, 256, 0, st>>>(src, N, L.nchunks, L.cols_per_chunk, diag, pos, perm, cval,
+                                                       cpos, cidx, errsum, ctrl);
+      return check_launch("k_pc_init");
+    case 1:
+      LOB_REQUIRE(Lt && perm && pi64, "lob_pivchol_rows_pivot: NULL pointer");
+      LOB_REQUIRE(m >= 0 && m < rankmax, "lob_pivchol_rows_pivot: step out of range");
+      k_pc_pivot<T><<<1, 1024, 0, st>>>(B, N, rankmax, m, L.nchunks, tol, cval, cpos, cidx, errsum, orig, pos, perm,
+                                        pi, piv, Lt, ctrl, pi64);
+      return check_launch("k_pc_pivot");
+    case 2:
+      LOB_REQUIRE(buf && Lt, "lob_pivchol_rows_update: NULL pointer");
+      LOB_REQUIRE(m >= 0 && m < rankmax, "lob_pivchol_rows_update: step out of range");
+      if (m + 1 < N) {
+        k_pc_update<T, RowBufSrc<T>><<<grid, 256, sizeof(T) * (size_t)rankmax, st>>>(
+            src, N, rankmax, m, L.nchunks, L.cols_per_chunk, diag, pos, pi, piv, Lt, cval, cpos, cidx, errsum, ctrl);
+        return check_launch("k_pc_update");
+      }
+      return LOB_OK;
+    default:
+      LOB_REQUIRE(m_out, "lob_pivchol_rows_status: NULL pointer");
+      k_pc_status<<<1, 1, 0, st>>>(ctrl, m_out, active_out);
+      return check_launch("k_pc_status");
+  }
+}
+}  // namespace lob
+
+extern "C" int lob_pivchol_rows_begin(int32_t dtype, int64_t B, int64_t N, int32_t rank, const void* diag,
+                                      int64_t* perm, void* ws, void* stream) {
+  LOB_DISPATCH_DTYPE(dtype, {
+    return pc_rows_step<scalar_t>(0, B, N, rank, 0, 0.0, (const scalar_t*)diag, nullptr, perm, nullptr, nullptr,
+                                  nullptr, ws, (cudaStream_t)stream);
+  });
+}
+extern "C" int lob_pivchol_rows_pivot(int32_t dtype, int64_t B, int64_t N, int32_t rank, int32_t m, double error_tol,
+                                      void* Lt, int64_t* perm, int64_t* pivot_rows, void* ws, void* stream) {
+  LOB_DISPATCH_DTYPE(dtype, {
+    return pc_rows_step<scalar_t>(1, B, N, rank, m, error_tol, nullptr, (scalar_t*)Lt, perm, pivot_rows, nullptr,
+                                  nullptr, ws, (cudaStream_t)stream);
+  });
+}
+extern "C" int lob_pivchol_rows_update(int32_t dtype, int64_t B, int64_t N, int32_t rank, int32_t m, const void* rows,
+                                       void* Lt, void* ws, void* stream) {
+  LOB_DISPATCH_DTYPE(dtype, {
+    return pc_rows_step<scalar_t>(2, B, N, rank, m, 0.0, (const scalar_t*)rows, (scalar_t*)Lt, nullptr, nullptr,
+                                  nullptr, nullptr, ws, (cudaStream_t)stream);
+  });
+}
+extern "C" int lob_pivchol_rows_status(int32_t dtype, int64_t B, int64_t N, int32_t rank, int32_t* m_out,
+                                       int32_t* active_out, void* ws, void* stream) {
+  LOB_DISPATCH_DTYPE(dtype, {
+    return pc_rows_step<scalar_t>(3, B, N, rank, 0, 0.0, nullptr, nullptr, nullptr, nullptr, m_out, active_out, ws,
+                                  (cudaStream_t)stream);
   });
 }

@@ -1,6 +1,8 @@
-"""PivotedCholesky Function (reference: functions/_pivoted_cholesky.py:13-105).  Forward only: the batched pivoted
-Cholesky runs in ``csrc/pivchol.cu`` with the operator's row source (dense / Kronecker / Toeplitz) as a device functor,
-so the reference's per-step ``__getitem__`` gathers and host synchronisations (:57-98) disappear."""
+"""PivotedCholesky Function (reference: functions/_pivoted_cholesky.py:13-105).  The batched pivoted Cholesky
+runs in ``csrc/pivchol.cu``.  Dense / Kronecker / Toeplitz operators hand the kernels a device functor as row source, so
+the reference's per-step ``__getitem__`` gathers and host synchronisations (:57-98) disappear; every other operator
+(Root, Sum, user classes) takes the reference's generic route -- one ``_get_indices`` row gather per step on
+device-resident pivot indices -- through the same kernels (``_kernels.pivoted_cholesky_rows``)."""
 from __future__ import annotations
 
 import torch
@@ -24,16 +26,7 @@ class PivotedCholesky(Function):
             settings.verbose_linalg.logger.debug(
                 f"Running Pivoted Cholesky on a {matrix.shape} RHS for {max_iter} iterations."
             )
-        impl = getattr(matrix, "_pivoted_cholesky", None)
-        if impl is None:
-            raise NotImplementedError(f"{matrix.__class__.__name__} has no device row source for pivoted Cholesky")
-        try:
-            L, perm = impl(max_iter, error_tol)
-        except NotImplementedError:
-            raise NotImplementedError(
-                f"pivoted Cholesky needs a device row source; {matrix.__class__.__name__} does not provide one "
-                "(supported: Dense, KroneckerProduct, Toeplitz)."
-            ) from None
+        L, perm = matrix._pivoted_cholesky(max_iter, error_tol)
         ctx.mark_non_differentiable(perm)
         return L, perm
 

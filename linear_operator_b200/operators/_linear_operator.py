@@ -125,6 +125,11 @@ class LinearOperator(object):
     def _get_indices(self, row_index, col_index, *batch_indices) -> Tensor:
         raise NotImplementedError(f"{self.__class__.__name__} does not implement _get_indices")
 
+    def _pivoted_cholesky(self, rank: int, error_tol: float):
+        """(L (*batch, N, m), permutation (*batch, N) int64).  Default: rows through ``_get_indices`` (the reference's
+        generic route, functions/_pivoted_cholesky.py:57-98); classes with a device row functor override this."""
+        return _kernels.pivoted_cholesky_rows(self, rank, error_tol)
+
     def _bilinear_derivative(self, left_vecs, right_vecs):
         raise NotImplementedError(
             "The backward pass of the Krylov path (functions/_inv_quad_logdet.py:163-226 of the reference) is a "

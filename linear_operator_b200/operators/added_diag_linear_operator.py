@@ -81,13 +81,18 @@ class AddedDiagLinearOperator(SumLinearOperator):
         if self._q_cache is None:
             max_iter = settings.max_preconditioner_size.value()
             self._piv_chol_self = self._linear_op.pivoted_cholesky(rank=max_iter)
-            if torch.any(torch.isnan(self._piv_chol_self)).item():  # :126-131
+            self._init_cache()
+            # ONE host read for both failure modes: NaNs in the pivoted-Cholesky factor (:126-131) and a non-positive
+            # pivot in the k x k factorisation behind Q (the reference's QR would hand back NaNs for it).  The read is
+            # issued after the whole build has been queued, so the device keeps working while the host waits.
+            bad = torch.isnan(self._piv_chol_self).any() | self._q_cache.info.ne(0).any()
+            if bad.item():
+                self._q_cache = self._precond_lt = self._precond_logdet_cache = None
                 warnings.warn(
                     "NaNs encountered in preconditioner computation. Attempting to continue without preconditioning.",
                     NumericalWarning,
                 )
                 return None, None, None
-            self._init_cache()
         return self._q_cache, self._precond_lt, self._precond_logdet_cache
 
     def _init_cache(self):  # :144-184
@@ -104,9 +109,6 @@ class AddedDiagLinearOperator(SumLinearOperator):
 
     def _diagonal(self):
         return self._linear_op._diagonal() + self._diag_tensor._diagonal()
-
-    def _pivoted_cholesky(self, rank, error_tol):
-        raise NotImplementedError
 
 
 __all__ = ["AddedDiagLinearOperator"]

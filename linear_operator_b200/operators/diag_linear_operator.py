@@ -68,9 +68,6 @@ class DiagLinearOperator(LinearOperator):
         base = torch.randn(num_samples, *self._diag.shape, dtype=self.dtype, device=self.device)
         return base * self._diag.sqrt()
 
-    def _pivoted_cholesky(self, rank, error_tol):
-        raise NotImplementedError("pivoted Cholesky of a diagonal operator is outside the Krylov path")
-
 
 class ConstantDiagLinearOperator(DiagLinearOperator):
     """Diagonal with one value per batch element: ``diag_values`` is ``(*batch, 1)`` (reference :300-350)."""

@@ -56,11 +56,6 @@ class RootLinearOperator(LinearOperator):
         samples = _kernels.matmul_nn(R, base)  # (*batch, N, S)
         return samples.permute(-1, *range(self.dim() - 1)).contiguous()
 
-    def _pivoted_cholesky(self, rank, error_tol):
-        # rows of R R^T through the dense-row functor on the materialised product would cost N^2; use the generic
-        # closure-based driver instead
-        raise NotImplementedError
-
 
 class LowRankRootLinearOperator(RootLinearOperator):
     """A RootLinearOperator whose root has few columns; adding a diagonal yields the Woodbury operator

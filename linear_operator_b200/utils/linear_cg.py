@@ -21,6 +21,7 @@ def _default_preconditioner(x):
     return x.clone()
 
 
+@_lib.device_guard
 def linear_cg(
     matmul_closure,
     rhs,

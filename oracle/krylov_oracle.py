@@ -706,3 +706,56 @@ def dense_added_diag_inv_quad_logdet_backward(A, d, rhs, probes, grad_inv_quad, 
         grad_d = grad_d + np.asarray(grad_logdet)[..., None] * np.diagonal(Pinv, axis1=-1, axis2=-2)
         grad_A = grad_A + pivoted_cholesky_backward(A, perm, L.shape[-1], grad_L)
     return grad_A, grad_d, grad_rhs
+
+
+# ------------------------------------------------------------------------------------------------
+# Round-2 additions: generic-operator rows, Solve / InvQuad backward, symmetric-Toeplitz derivative
+# ------------------------------------------------------------------------------------------------
+def root_rows(U, idx):
+    """rows ``idx (*batch,)`` of U U^T through RootLinearOperator._get_indices (root_linear_operator.py:47-58):
+    (U[row] * U[col]).sum(-1)."""
+    Ub = np.broadcast_to(U, idx.shape + U.shape[-2:])
+    left = np.take_along_axis(Ub, idx[..., None, None].repeat(U.shape[-1], axis=-1), axis=-2)  # (*b, 1, r)
+    return (left * Ub).sum(-1)
+
+
+def sym_toeplitz_derivative_quadratic_form(left, right):
+    """res[..., i] = sum_j u_j^T (dT/dc_i) v_j for left / right (*b, N, C): ones on the i-th sub- and super-diagonal
+    (utils/toeplitz.py:164-204; restated as the two cross-correlations it computes through Toeplitz products)."""
+    n = left.shape[-2]
+    res = np.zeros(left.shape[:-2] + (n,), left.dtype)
+    for i in range(n):
+        a = (left[..., : n - i, :] * right[..., i:, :]).sum((-2, -1))
+        b = (left[..., i:, :] * right[..., : n - i, :]).sum((-2, -1))
+        res[..., i] = a + b if i > 0 else a
+    return res
+
+
+def dense_added_diag_solve_backward(A, d, rhs, grad_out, solve_fn, lhs=None):
+    """Solve.backward for AddedDiag(Dense(A), Diag(d)) (functions/_solve.py:70-131).  ``solve_fn(b)`` is the forward
+    solve K^-1 b of the same call (preconditioned CG).  Returns (grad_A, grad_d, grad_rhs, grad_lhs)."""
+    if lhs is None:
+        right_solves = solve_fn(rhs)                                   # saved `solves` (:54)
+        left_solves = solve_fn(grad_out)                               # Solve.apply(..., grad_output) (:96)
+        grad_lhs = None
+    else:
+        solves = solve_fn(np.concatenate([np.swapaxes(lhs, -1, -2), rhs], -1))   # :48-49
+        nl = lhs.shape[-2]
+        right_solves = solves[..., nl:]
+        left_solves = solves[..., :nl] @ grad_out                      # :113
+        grad_lhs = grad_out @ np.swapaxes(right_solves, -1, -2)        # :116
+    L = np.concatenate([left_solves, right_solves], -1)                # :104-107 / :119-122
+    R = -0.5 * np.concatenate([right_solves, left_solves], -1)
+    grad_A = L @ np.swapaxes(R, -1, -2)                                # dense_linear_operator.py:69-71
+    grad_d = (L * R).sum(-1)                                           # diag_linear_operator.py:37-45
+    return grad_A, grad_d, left_solves, grad_lhs
+
+
+def dense_added_diag_inv_quad_backward(A, d, rhs, grad_out, solve_fn):
+    """InvQuad.backward (functions/_inv_quad.py:63-93); grad_out (*b, C) weights the un-reduced inverse quadratic
+    forms.  Returns (grad_A, grad_d, grad_rhs)."""
+    solves = solve_fn(rhs)
+    neg = -solves * grad_out[..., None, :]
+    grad_A = neg @ np.swapaxes(solves, -1, -2)
+    grad_d = (neg * solves).sum(-1)
+    return grad_A, grad_d, -2.0 * neg
