@@ -275,6 +275,30 @@ int lob_lanczos_init(int32_t dtype, int64_t B, int64_t N, int64_t C, const void*
 int lob_lanczos_step(int32_t dtype, int32_t mode, int64_t B, int64_t N, int64_t C, int32_t t_cap, int32_t k,
                      const void* w, void* q_mat, void* t_mat, int32_t* flags, double tol, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Backward pass (functions/_inv_quad_logdet.py:163-226, _solve.py:70-131, _inv_quad.py:63-93,
+ * _pivoted_cholesky.py:106-150)
+ * ---------------------------------------------------------------------------------------------------------- */
+/* DenseLinearOperator._bilinear_derivative (dense_linear_operator.py:69-71) with the per-column scalings of the
+ * callers folded in:  out[b,i,j] (+)= sum_c w[b,c] * left[b,i,c] * right[b,j,c];  left (B,N,C), right (B,M,C),
+ * w (B,C) or NULL (= 1), out (B,N,M); accumulate != 0 adds to out. */
+int lob_bilinear_dense(int32_t dtype, int64_t B, int64_t N, int64_t M, int64_t C, const void* left, const void* right,
+                       const void* w, void* out, int32_t accumulate, void* stream);
+/* DiagLinearOperator._bilinear_derivative (diag_linear_operator.py:37-45): out[b,n] = sum_c w[b,c] left[b,n,c] right[b,n,c] */
+int lob_bilinear_diag(int32_t dtype, int64_t B, int64_t N, int64_t C, const void* left, const void* right,
+                      const void* w, void* out, void* stream);
+/* out (B,k,k) = inverse of the lower-triangular k x k blocks Cm[b] (leading dimension ldc, batch stride in elements):
+ * the triangular-solve adjoint of PivotedCholesky.backward (_pivoted_cholesky.py:128-137). */
+int lob_tri_inverse(int32_t dtype, int64_t B, int32_t k, const void* Cm, int64_t ldc, int64_t c_batch_stride, void* out,
+                    void* stream);
+/* sym_toeplitz_derivative_quadratic_form (utils/toeplitz.py:164-204) in the frequency domain: fu, fv (B,C,H) complex
+ * spectra (cuFFT R2C of the zero-padded left / right vectors), out (B,H) complex = sum_c w[b,c] 2 Re(conj(fu) fv);
+ * finish: out (B,N) = scale * y[b, :N] with element 0 halved (y (B,L) = C2R of the spectrum). */
+int lob_toeplitz_cross_spectrum(int32_t dtype, int64_t B, int64_t C, int64_t H, const void* fu, const void* fv,
+                                const void* w, void* out, void* stream);
+int lob_toeplitz_deriv_finish(int32_t dtype, int64_t B, int64_t N, int64_t L, const void* y, double scale, void* out,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -610,6 +610,105 @@ def lanczos_step(mode: int, k: int, w: Optional[torch.Tensor], q_mat: torch.Tens
     )
 
 
+# ------------------------------------------------------------------------------------------------------------
+# backward pass
+# ------------------------------------------------------------------------------------------------------------
+def _col_weights(w: Optional[torch.Tensor], batch_shape, C: int, like: torch.Tensor):
+    if w is None:
+        return None
+    return w.to(like.dtype).expand(*batch_shape, C).reshape(-1, C).contiguous()
+
+
+def bilinear_dense(left: torch.Tensor, right: torch.Tensor, w: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sum_c w[..., c] left[..., :, c] right[..., :, c]^T  -> (*b, N, M): DenseLinearOperator._bilinear_derivative
+    (dense_linear_operator.py:69-71) with the callers' column scalings folded in.  ``out``: accumulate into it."""
+    require_cuda(left, right, w, out)
+    lib = _lib.load()
+    batch_shape = torch.broadcast_shapes(left.shape[:-2], right.shape[:-2])
+    N, C = left.shape[-2:]
+    M = right.shape[-2]
+    if right.shape[-1] != C:
+        raise RuntimeError(f"Size mismatch: {tuple(left.shape)} vs {tuple(right.shape)}")
+    Lf = _flat3(left.expand(*batch_shape, N, C))
+    Rf = _flat3(right.expand(*batch_shape, M, C))
+    B = Lf.shape[0]
+    wf = _col_weights(w, batch_shape, C, left)
+    acc = 1
+    if out is None:
+        out = torch.empty(B, N, M, dtype=left.dtype, device=left.device)
+        acc = 0
+    elif not out.is_contiguous() or out.numel() != B * N * M:
+        raise _lib.LobError("bilinear_dense: `out` must be a contiguous (*batch, N, M) tensor")
+    check(lib.lob_bilinear_dense(dt(left), B, N, M, C, ptr(Lf), ptr(Rf), ptr(wf), ptr(out), acc, stream(left)),
+          "lob_bilinear_dense")
+    return out.reshape(*batch_shape, N, M)
+
+
+def bilinear_diag(left: torch.Tensor, right: torch.Tensor, w: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sum_c w[..., c] left[..., n, c] right[..., n, c] -> (*b, N)  (diag_linear_operator.py:37-45)."""
+    require_cuda(left, right, w)
+    lib = _lib.load()
+    batch_shape = torch.broadcast_shapes(left.shape[:-2], right.shape[:-2])
+    N, C = left.shape[-2:]
+    Lf = _flat3(left.expand(*batch_shape, N, C))
+    Rf = _flat3(right.expand(*batch_shape, N, C))
+    B = Lf.shape[0]
+    wf = _col_weights(w, batch_shape, C, left)
+    out = torch.empty(B, N, dtype=left.dtype, device=left.device)
+    check(lib.lob_bilinear_diag(dt(left), B, N, C, ptr(Lf), ptr(Rf), ptr(wf), ptr(out), stream(left)),
+          "lob_bilinear_diag")
+    return out.reshape(*batch_shape, N)
+
+
+def tri_inverse(Cm: torch.Tensor) -> torch.Tensor:
+    """Inverse of (a batch of) lower-triangular k x k matrices."""
+    require_cuda(Cm)
+    lib = _lib.load()
+    k = Cm.shape[-1]
+    Cf = _flat3(Cm)
+    out = torch.empty_like(Cf)
+    check(lib.lob_tri_inverse(dt(Cm), Cf.shape[0], k, ptr(Cf), k, k * k, ptr(out), stream(Cm)), "lob_tri_inverse")
+    return out.reshape(Cm.shape)
+
+
+def toeplitz_bilinear_derivative(left: torch.Tensor, right: torch.Tensor, w: Optional[torch.Tensor] = None):
+    """res[..., i] = sum_c w_c u_c^T (dT/dc_i) v_c, the gradient of a symmetric Toeplitz operator's column
+    (utils/toeplitz.py:164-204; the reference runs two Toeplitz products per column): cross-correlations through a
+    zero-padded real FFT of length L >= 2N, summed over the columns in the frequency domain."""
+    require_cuda(left, right, w)
+    lib = _lib.load()
+    batch_shape = torch.broadcast_shapes(left.shape[:-2], right.shape[:-2])
+    N, C = left.shape[-2:]
+    L = _next_pow2(2 * N)
+    Lf = _flat3(left.expand(*batch_shape, N, C))
+    Rf = _flat3(right.expand(*batch_shape, N, C))
+    B = Lf.shape[0]
+    wf = _col_weights(w, batch_shape, C, left)
+    out = torch.empty(B, N, dtype=left.dtype, device=left.device)
+    chunk = max(1, min(B, int(TOEPLITZ_SCRATCH_BYTES // (C * L * left.element_size()))))
+    for b0 in range(0, B, chunk):
+        b1 = min(B, b0 + chunk)
+        nb = b1 - b0
+        spectra = []
+        for X in (Lf, Rf):
+            xt = torch.empty(nb, C, L, dtype=left.dtype, device=left.device)
+            check(lib.lob_toeplitz_pad(dt(left), nb, N, C, L, ptr(X[b0:b1]), ptr(xt), stream(left)), "lob_toeplitz_pad")
+            spectra.append(torch.fft.rfft(xt))
+            del xt
+        fu, fv = spectra
+        H = fu.shape[-1]
+        spec = torch.empty(nb, H, dtype=fu.dtype, device=left.device)
+        check(lib.lob_toeplitz_cross_spectrum(dt(left), nb, C, H, ptr(fu), ptr(fv),
+                                              ptr(None if wf is None else wf[b0:b1]), ptr(spec), stream(left)),
+              "lob_toeplitz_cross_spectrum")
+        del fu, fv, spectra
+        y = torch.fft.irfft(spec, n=L, norm="forward")  # un-normalised C2R; the 1/L goes into the finishing kernel
+        check(lib.lob_toeplitz_deriv_finish(dt(left), nb, N, L, ptr(y), 1.0 / L, ptr(out[b0:b1]), stream(left)),
+              "lob_toeplitz_deriv_finish")
+    return out.reshape(*batch_shape, N)
+
+
 # Every launch goes to the current stream of the tensors' own device; make that device current for the duration of the
 # call when the caller's current device is another one (multi-GPU processes).
 for _name, _obj in list(globals().items()):

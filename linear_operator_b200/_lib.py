@@ -145,6 +145,11 @@ _SIGS = {
     ),
     "lob_cap_solve_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int64]),
     "lob_cap_solve": (ctypes.c_int, [c_int32, c_int64, c_int32, c_int64, _P, c_int64, _P, _P, _P, _P, _P]),
+    "lob_bilinear_dense": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int32, _P]),
+    "lob_bilinear_diag": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "lob_tri_inverse": (ctypes.c_int, [c_int32, c_int64, c_int32, _P, c_int64, c_int64, _P, _P]),
+    "lob_toeplitz_cross_spectrum": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "lob_toeplitz_deriv_finish": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, c_double, _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

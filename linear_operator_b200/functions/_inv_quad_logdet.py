@@ -7,7 +7,6 @@ from torch.autograd import Function
 
 from .. import _kernels, settings
 from ..utils.stochastic_lq import StochasticLQ
-from ._pivoted_cholesky import _BACKWARD_MSG
 
 
 def _draw_probes(precond_lt, num_probes):
@@ -52,6 +51,11 @@ class InvQuadLogdet(Function):
         else:
             matrix_args, precond_args = args, ()
 
+        ctx.representation_tree = representation_tree
+        ctx.precond_representation_tree = precond_representation_tree
+        ctx.preconditioner = preconditioner
+        ctx.inv_quad = inv_quad
+        ctx.num_precond_args = num_precond_args
         linear_op = representation_tree(*matrix_args)
         precond_lt = precond_representation_tree(*precond_args)
         dtype, device = linear_op.dtype, linear_op.device
@@ -68,9 +72,11 @@ class InvQuadLogdet(Function):
         num_random_probes = probe_vectors.size(-1)
         rhs_list = [probe_vectors]  # probes FIRST (:118)
         num_inv_quad_solves = 0
+        ctx.is_vector = False
         if inv_quad:
             if inv_quad_rhs.ndimension() == 1:
                 inv_quad_rhs = inv_quad_rhs.unsqueeze(-1)
+                ctx.is_vector = True
             rhs_list.append(inv_quad_rhs)
             num_inv_quad_solves = inv_quad_rhs.size(-1)
         rhs = torch.cat(rhs_list, -1)  # :132
@@ -84,9 +90,60 @@ class InvQuadLogdet(Function):
                 logdet_term = torch.tensor(float("nan"), dtype=dtype, device=device)
         if inv_quad:  # :151-153
             inv_quad_term = _kernels.col_dots(solves, num_random_probes, inv_quad_rhs, 0, num_inv_quad_solves)
-        ctx.mark_non_differentiable(inv_quad_term, logdet_term)
+        ctx.probe_vectors, ctx.probe_vector_norms = probe_vectors, probe_vector_norms
+        ctx.num_random_probes, ctx.num_inv_quad_solves = num_random_probes, num_inv_quad_solves
+        ctx.save_for_backward(*precond_args, *matrix_args, solves)  # :155-158
         return inv_quad_term, logdet_term
 
     @staticmethod
     def backward(ctx, inv_quad_grad_output, logdet_grad_output):
-        raise NotImplementedError(_BACKWARD_MSG.format("InvQuadLogdet", "_inv_quad_logdet.py:163-226"))
+        """Reference :163-226.  The probe solves stand in for K^-1 in the log-determinant's gradient; every operator
+        gradient is a ``_bilinear_derivative(left, right)`` call (a rank-C outer-product kernel for dense operators),
+        the preconditioner's tensors get theirs through ``precond_lt._bilinear_derivative`` (:209-211)."""
+        if ctx.num_precond_args:
+            precond_args = ctx.saved_tensors[: ctx.num_precond_args]
+            matrix_args = ctx.saved_tensors[ctx.num_precond_args: -1]
+        else:
+            precond_args = []
+            matrix_args = ctx.saved_tensors[:-1]
+        solves = ctx.saved_tensors[-1]
+        linear_op = ctx.representation_tree(*matrix_args)
+        precond_lt = ctx.precond_representation_tree(*precond_args)
+
+        if ctx.inv_quad:
+            inv_quad_grad_output = inv_quad_grad_output.unsqueeze(-2)  # (*b, 1, R)
+        logdet_grad_output = logdet_grad_output.unsqueeze(-1).unsqueeze(-1)  # (*b, 1, 1)
+
+        s = ctx.num_random_probes
+        coef = 1.0 / ctx.probe_vectors.size(-1)  # :181
+        probe_vector_solves = solves.narrow(-1, 0, s) * (ctx.probe_vector_norms * logdet_grad_output * coef)  # :182-183
+        unnormed = ctx.probe_vectors * ctx.probe_vector_norms
+        if ctx.preconditioner is not None:  # :187-190: probes now ~ N(0, P^-1)
+            precond_probe_vectors = ctx.preconditioner(unnormed)
+        else:
+            precond_probe_vectors = unnormed
+
+        left_factors_list = [probe_vector_solves]
+        right_factors_list = [precond_probe_vectors]
+        neg_inv_quad_solves_times_grad_out = None
+        if ctx.inv_quad:  # :198-202
+            inv_quad_solves = solves.narrow(-1, s, ctx.num_inv_quad_solves)
+            neg_inv_quad_solves_times_grad_out = inv_quad_solves * inv_quad_grad_output.neg()
+            left_factors_list.append(neg_inv_quad_solves_times_grad_out)
+            right_factors_list.append(inv_quad_solves)
+        left_factors = torch.cat(left_factors_list, -1)
+        right_factors = torch.cat(right_factors_list, -1)
+        matrix_arg_grads = linear_op._bilinear_derivative(left_factors, right_factors)  # :206
+
+        precond_arg_grads = precond_lt._bilinear_derivative(  # :209-211
+            precond_probe_vectors * (-coef), precond_probe_vectors * logdet_grad_output
+        )
+
+        if ctx.inv_quad:  # :213-218
+            inv_quad_rhs_grad = neg_inv_quad_solves_times_grad_out * -2.0
+            if ctx.is_vector:
+                inv_quad_rhs_grad = inv_quad_rhs_grad.squeeze(-1)
+            res = [inv_quad_rhs_grad] + list(matrix_arg_grads) + list(precond_arg_grads)
+        else:
+            res = list(matrix_arg_grads) + list(precond_arg_grads)
+        return tuple([None] * 7 + res)

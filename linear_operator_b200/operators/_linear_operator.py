@@ -130,10 +130,16 @@ class LinearOperator(object):
         generic route, functions/_pivoted_cholesky.py:57-98); classes with a device row functor override this."""
         return _kernels.pivoted_cholesky_rows(self, rank, error_tol)
 
-    def _bilinear_derivative(self, left_vecs, right_vecs):
+    def _bilinear_derivative(self, left_vecs: Tensor, right_vecs: Tensor) -> Tuple[Optional[Tensor], ...]:
+        """d/d(theta) sum_i u_i^T K(theta) v_i for every tensor of ``representation()`` (reference :336-393).  The
+        reference's default differentiates ``_matmul`` with autograd; the ``_matmul``s of this package are CUDA kernels
+        outside autograd, so every operator class of the path carries its closed form and a user-defined operator that
+        wants gradients overrides this hook (the reference's own extension point)."""
+        if not any(a.requires_grad for a in self.representation()):
+            return (None,) * len(self.representation())
         raise NotImplementedError(
-            "The backward pass of the Krylov path (functions/_inv_quad_logdet.py:163-226 of the reference) is a "
-            "'next' row of the scope table (SURVEY.md section 8f) and is not built yet."
+            f"{self.__class__.__name__} must implement _bilinear_derivative(left_vecs, right_vecs) to be "
+            "differentiated through the Krylov path."
         )
 
     def _preconditioner(self) -> Tuple[Optional[Callable], Optional["LinearOperator"], Optional[Tensor]]:

@@ -16,6 +16,43 @@ from .root_linear_operator import RootLinearOperator
 from .sum_linear_operator import PsdSumLinearOperator, SumLinearOperator
 
 
+class _PreconditionerLogdet(torch.autograd.Function):
+    """log det(L L^T + D) as a differentiable function of the pivoted-Cholesky factor and the diagonal.  The reference
+    gets this gradient from autograd through its QR (added_diag_linear_operator.py:164-183); here the value comes out
+    of the Gram/Cholesky kernels and the gradient is the closed form d/dL = 2 P^-1 L, d/dD = diag(P^-1) with
+    P^-1 = D^-1 - Q Q^T applied by the same preconditioner kernels.  For a constant diagonal the reference differentiates
+    w.r.t. the ONE value it keeps (``noise.narrow(-2, 0, 1)``, :161), i.e. d/d sigma^2 = tr(P^-1): reproduced, so the
+    gradient lands where the reference's does."""
+
+    @staticmethod
+    def forward(ctx, precond, L, noise):
+        ctx.precond = precond
+        ctx.noise_shape = noise.shape
+        ctx.save_for_backward(L)
+        return precond.logdet.clone()
+
+    @staticmethod
+    def backward(ctx, grad):
+        (L,) = ctx.saved_tensors
+        pre = ctx.precond
+        g = grad.reshape(-1)  # (B,)
+        B, N = pre.Q.shape[0], pre.N
+        grad_L = grad_noise = None
+        if ctx.needs_input_grad[1]:
+            pinv_l = pre(L.detach())  # P^-1 L through the preconditioner kernels, (*b, N, k)
+            grad_L = pinv_l * (2.0 * grad).reshape(*grad.shape, 1, 1)
+        if ctx.needs_input_grad[2]:
+            rowsq = _kernels.bilinear_diag(pre.Q, pre.Q)  # (B, N): diag(Q Q^T)
+            if pre.constant:
+                sig = pre.noise[:, 0]
+                grad_noise = (g * (N - rowsq.sum(-1)) / sig).reshape(*grad.shape, 1)
+            else:
+                grad_noise = (g.unsqueeze(-1) * (pre.noise.reciprocal() - rowsq)).reshape(*grad.shape, N)
+            if grad_noise.shape != ctx.noise_shape:
+                grad_noise = grad_noise.sum_to_size(ctx.noise_shape)
+        return None, grad_L, grad_noise
+
+
 class AddedDiagLinearOperator(SumLinearOperator):
     """``linear_op + diag``; exactly one of the two operands must be a DiagLinearOperator (reference :36-70)."""
 
@@ -103,8 +140,12 @@ class AddedDiagLinearOperator(SumLinearOperator):
             # the reference decides "constant" at run time by comparing with the first element (:149-150)
             self._constant_diag = bool(torch.equal(diag, diag[..., :1].expand_as(diag)))
         self._noise = diag[..., :1] if self._constant_diag else diag
-        self._q_cache = _kernels.AddedDiagPreconditioner(self._piv_chol_self, diag, self._constant_diag)
+        with torch.no_grad():
+            self._q_cache = _kernels.AddedDiagPreconditioner(self._piv_chol_self, diag, self._constant_diag)
         self._precond_logdet_cache = self._q_cache.logdet
+        if torch.is_grad_enabled() and (self._piv_chol_self.requires_grad or diag.requires_grad):
+            # logdet_P is added to the estimate (operators/_linear_operator.py:1799-1800) and is part of the graph
+            self._precond_logdet_cache = _PreconditionerLogdet.apply(self._q_cache, self._piv_chol_self, self._noise)
         self._precond_lt = PsdSumLinearOperator(RootLinearOperator(self._piv_chol_self), self._diag_tensor)  # :159
 
     def _diagonal(self):

@@ -35,6 +35,16 @@ class DenseLinearOperator(LinearOperator):
         closure.fused = lambda v: _kernels.dense_matmul(tsr, v, want_dots=True)
         return closure
 
+    def _bilinear_derivative(self, left_vecs, right_vecs):  # :69-71: left right^T, one rank-C outer-product kernel
+        if not self.tensor.requires_grad:  # a (*batch, M, N) gradient nobody asked for is the costliest thing to skip
+            return (None,)
+        if left_vecs.dim() == 1:
+            left_vecs, right_vecs = left_vecs.unsqueeze(-1), right_vecs.unsqueeze(-1)
+        res = _kernels.bilinear_dense(left_vecs, right_vecs)
+        if res.shape != self.tensor.shape:  # operator batch smaller than the vectors' batch: collapse the broadcast
+            res = res.sum_to_size(self.tensor.shape)
+        return (res,)
+
     def _size(self):
         return self.tensor.size()
 

@@ -33,6 +33,16 @@ class DiagLinearOperator(LinearOperator):
     def _expand_batch(self, batch_shape):
         return self.__class__(self._diag.expand(*batch_shape, self._diag.size(-1)))
 
+    def _bilinear_derivative(self, left_vecs, right_vecs):  # :37-45
+        if not self._diag.requires_grad:
+            return (None,)
+        if left_vecs.dim() == 1:
+            left_vecs, right_vecs = left_vecs.unsqueeze(-1), right_vecs.unsqueeze(-1)
+        res = _kernels.bilinear_diag(left_vecs, right_vecs)
+        if res.shape != self._diag.shape:
+            res = res.sum_to_size(self._diag.shape)
+        return (res,)
+
     def _get_indices(self, row_index, col_index, *batch_indices):  # :73-78
         res = self._diag[(*batch_indices, row_index)]
         return res * torch.eq(row_index, col_index).to(device=res.device, dtype=res.dtype)
@@ -89,6 +99,16 @@ class ConstantDiagLinearOperator(DiagLinearOperator):
 
     def _expand_batch(self, batch_shape):
         return self.__class__(self.diag_values.expand(*batch_shape, 1), diag_shape=self.diag_shape)
+
+    def _bilinear_derivative(self, left_vecs, right_vecs):  # :337-344
+        if not self.diag_values.requires_grad:
+            return (None,)
+        if left_vecs.dim() == 1:
+            left_vecs, right_vecs = left_vecs.unsqueeze(-1), right_vecs.unsqueeze(-1)
+        res = _kernels.bilinear_diag(left_vecs, right_vecs).sum(-1, keepdim=True)
+        if res.shape != self.diag_values.shape:
+            res = res.sum_to_size(self.diag_values.shape)
+        return (res,)
 
     def add_diagonal(self, added_diag):
         if added_diag.dim() == 0 or added_diag.size(-1) == 1:

@@ -45,6 +45,9 @@ class IdentityLinearOperator(ConstantDiagLinearOperator):
     def zero_mean_mvn_samples(self, num_samples):  # :262-266
         return torch.randn(num_samples, *self._batch_shape, self.diag_shape, dtype=self._dtype, device=self._device)
 
+    def _bilinear_derivative(self, left_vecs, right_vecs):
+        return ()
+
     def logdet(self):
         return torch.zeros(self._batch_shape, dtype=self._dtype, device=self._device)
 

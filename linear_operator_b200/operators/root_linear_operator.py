@@ -24,6 +24,18 @@ class RootLinearOperator(LinearOperator):
         R = self._root_tensor()
         return _kernels.matmul_nn(R, _kernels.tn_matmul(R, rhs))
 
+    def _bilinear_derivative(self, left_vecs, right_vecs):
+        """d/dR sum_i u_i^T R R^T v_i = U (R^T V)^T + V (R^T U)^T -- what the reference's autograd default (:336-393)
+        yields for ``_matmul = R (R^T .)``; the root is itself an operator and receives both terms through ITS hook."""
+        if left_vecs.dim() == 1:
+            left_vecs, right_vecs = left_vecs.unsqueeze(-1), right_vecs.unsqueeze(-1)
+        R = self._root_tensor()
+        rt_right = _kernels.tn_matmul(R, right_vecs)  # (*, r, C)
+        rt_left = _kernels.tn_matmul(R, left_vecs)
+        a = self.root._bilinear_derivative(left_vecs, rt_right)
+        b = self.root._bilinear_derivative(right_vecs, rt_left)
+        return tuple(None if x is None else x + y for x, y in zip(a, b))
+
     def _size(self):
         n = self.root.size(-2)
         return torch.Size((*self.root.batch_shape, n, n))

@@ -22,6 +22,11 @@ class SumLinearOperator(LinearOperator):
             out = out.add_(op._matmul(rhs))
         return out
 
+    def _bilinear_derivative(self, left_vecs, right_vecs):  # :59-62
+        return tuple(
+            var for linear_op in self.linear_ops for var in linear_op._bilinear_derivative(left_vecs, right_vecs)
+        )
+
     def _size(self):
         return self.linear_ops[0].size()
 

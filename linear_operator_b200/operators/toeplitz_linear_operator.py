@@ -33,6 +33,14 @@ class ToeplitzLinearOperator(LinearOperator):
         """T X + d (.) X with the diagonal folded into the un-padding kernel."""
         return _kernels.toeplitz_matmul(self.column, rhs, d=diag, fc_cache=self._spectrum())
 
+    def _bilinear_derivative(self, left_vecs, right_vecs):  # :55-66 -> utils/toeplitz.py:164-204
+        if left_vecs.dim() == 1:
+            left_vecs, right_vecs = left_vecs.unsqueeze(-1), right_vecs.unsqueeze(-1)
+        res = _kernels.toeplitz_bilinear_derivative(left_vecs, right_vecs)
+        if res.shape != self.column.shape:  # collapse expanded broadcast dimensions (:63-64)
+            res = res.sum_to_size(self.column.shape)
+        return (res,)
+
     def _size(self):
         return torch.Size((*self.column.shape, self.column.size(-1)))
 

@@ -703,7 +703,14 @@ def dense_added_diag_inv_quad_logdet_backward(A, d, rhs, probes, grad_inv_quad, 
         P = L @ Lt + d[..., None] * np.eye(n, dtype=A.dtype)
         Pinv = np.linalg.inv(P)
         grad_L = grad_L + np.asarray(grad_logdet)[..., None, None] * 2.0 * (Pinv @ L)
-        grad_d = grad_d + np.asarray(grad_logdet)[..., None] * np.diagonal(Pinv, axis1=-1, axis2=-2)
+        dinv = np.diagonal(Pinv, axis1=-1, axis2=-2)
+        if np.array_equal(d, np.broadcast_to(d[..., :1], d.shape)):
+            # constant diagonal: the reference keeps ONE noise value, `noise.narrow(-2, 0, 1)`
+            # (added_diag_linear_operator.py:161), so d logdet_P / d sigma^2 = tr(P^-1) lands on element 0
+            grad_d = grad_d.copy()
+            grad_d[..., 0] += np.asarray(grad_logdet) * dinv.sum(-1)
+        else:
+            grad_d = grad_d + np.asarray(grad_logdet)[..., None] * dinv
         grad_A = grad_A + pivoted_cholesky_backward(A, perm, L.shape[-1], grad_L)
     return grad_A, grad_d, grad_rhs
 

@@ -199,6 +199,39 @@ def backward_cases():
          grad_rhs=npy(rhs.grad))
 
 
+def backward_constant_diag_cases():
+    """Constant diagonals: the reference keeps ONE noise value (added_diag_linear_operator.py:161), so the gradient of
+    logdet_P w.r.t. a (B, N) all-equal diagonal lands on element 0 only; with a ConstantDiagLinearOperator it lands on
+    diag_values."""
+    from linear_operator.operators import ConstantDiagLinearOperator
+
+    g = torch.Generator().manual_seed(71)
+    dt = torch.float64
+    n, s = 60, 6
+    for tag in ("full", "constop"):
+        w = torch.randn(2, n, 20, dtype=dt, generator=g)
+        k = (w @ w.mT / 20).requires_grad_(True)
+        rhs = torch.randn(2, n, 2, dtype=dt, generator=g).requires_grad_(True)
+        probes = unit_probes(2, n, s, dtype=dt, gen=g)
+        w_iq = torch.randn(2, dtype=dt, generator=g)
+        w_ld = torch.randn(2, dtype=dt, generator=g)
+        if tag == "full":
+            d = torch.full((2, n), 0.4, dtype=dt).requires_grad_(True)
+            diag_op = DiagLinearOperator(d)
+        else:
+            d = torch.tensor([[0.4], [0.7]], dtype=dt).requires_grad_(True)
+            diag_op = ConstantDiagLinearOperator(d, diag_shape=n)
+        op = _Injected(DenseLinearOperator(k), diag_op)
+        op.probes = probes
+        with settings.max_cholesky_size(0), settings.min_preconditioning_size(4), settings.max_preconditioner_size(6), \
+                settings.cg_tolerance(1e-10), settings.max_cg_iterations(400):
+            iq, ld = op.inv_quad_logdet(rhs, logdet=True)
+            (w_iq * iq + w_ld * ld).sum().backward()
+        save("backward_dense_const_" + tag + "_f64", A=npy(k), d=npy(d), rhs=npy(rhs), probes=npy(probes), w_iq=npy(w_iq),
+             w_ld=npy(w_ld), inv_quad=npy(iq), logdet=npy(ld), grad_A=npy(k.grad), grad_d=npy(d.grad),
+             grad_rhs=npy(rhs.grad), rank=6)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     cfg1()
@@ -206,3 +239,4 @@ if __name__ == "__main__":
     pivot_cases()
     toeplitz_cases()
     backward_cases()
+    backward_constant_diag_cases()

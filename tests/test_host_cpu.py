@@ -186,14 +186,23 @@ def test_preconditioner_gating_and_torch_function():
     with pytest.raises(NotImplementedError, match="is not implemented"):
         torch.trace(small)
     assert torch.equal(torch.diagonal(DiagLinearOperator(torch.arange(4.0)), dim1=-2, dim2=-1), torch.arange(4.0))
-    with pytest.raises(NotImplementedError, match="next"):
-        small._bilinear_derivative(None, None)
+    # no tensor requires grad: nothing to differentiate (reference _linear_operator.py:377-378)
+    assert small._bilinear_derivative(None, None) == (None, None)
+
+    class NoDerivative(lo.LinearOperator):
+        def __init__(self, t):
+            super().__init__(t)
+
+    with pytest.raises(NotImplementedError, match="_bilinear_derivative"):
+        NoDerivative(torch.eye(3, requires_grad=True))._bilinear_derivative(None, None)
     assert lo.to_dense(torch.eye(2)).shape == (2, 2) and type(lo.to_linear_operator(torch.eye(2))) is DenseLinearOperator
 
 
 def test_bench_reference_arm_prints_one_json_line():
-    """bench.py --impl reference (the oracle port timed on the host cores) keeps the driver's contract: exactly one JSON
-    line on stdout with the shared metric / config keys, impl = reference, a cpu_baseline and a zero-copy e2e object."""
+    """bench.py --impl reference (the unmodified reference from baseline/_ref on the host cores; the oracle port when
+    that install is absent) keeps the driver's contract: exactly one JSON line on stdout with the shared metric / config
+    keys, impl = reference, a cpu_baseline and a zero-copy e2e object.  Under torchrun (WORLD_SIZE > 1) rank 0 alone
+    prints, for the repo arm's global batch, with all host threads although torchrun exports OMP_NUM_THREADS=1."""
     import json
     import os
     import subprocess
@@ -212,6 +221,17 @@ def test_bench_reference_arm_prints_one_json_line():
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "calls/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    have_ref = os.path.isdir(os.path.join(root, "baseline", "_ref", "linear_operator"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["config"]["global_batch"] == 4
+    # torchrun environment: rank 1 is silent, rank 0 reports the global batch of the repo arm and its real thread count
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "0", "--cpu-sample-batch", "1", "--n", "300", "--batch", "4"]
+    env = dict(os.environ, WORLD_SIZE="2", RANK="1", LOCAL_RANK="1", OMP_NUM_THREADS="1")
+    assert subprocess.run(cmd, capture_output=True, text=True, timeout=300, check=True, env=env).stdout.strip() == ""
+    env["RANK"] = env["LOCAL_RANK"] = "0"
+    d2 = json.loads(subprocess.run(cmd, capture_output=True, text=True, timeout=300, check=True, env=env).stdout)
+    assert d2["config"]["global_batch"] == 8 and d2["n_gpus"] == 2
+    ncpu = len(os.sched_getaffinity(0))
+    assert d2["cpu_baseline"]["cores"] == ncpu or ncpu == 1
