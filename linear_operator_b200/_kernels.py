@@ -107,6 +107,61 @@ def dense_matmul(A: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = N
     return Y
 
 
+def gemm3x(A: torch.Tensor, B: torch.Tensor, trans_a: bool = False, trans_b: bool = False, alpha: float = 1.0,
+           row_alpha: Optional[torch.Tensor] = None, E: Optional[torch.Tensor] = None,
+           row_beta: Optional[torch.Tensor] = None, splits: int = 0, out_dtype: Optional[torch.dtype] = None,
+           a_div: int = 1, b_div: int = 1, batch: Optional[int] = None) -> Optional[torch.Tensor]:
+    """D[b] = ra * op(A[b // a_div]) op(B[b // b_div]) + rb * E[b] on the tensor cores (3xTF32, csrc/gemm3x.cu), BLAS-style:
+    A is stored (nb_a, M, K) -- (nb_a, K, M) with trans_a --, B is stored (nb_b, K, N) -- (nb_b, N, K) with trans_b;
+    the last dimension of either may be a strided view (leading dimension = stride of dim -2).  row_alpha / row_beta are
+    (batch, M) per-row factors.  Returns None when the layout is not TMA-addressable (caller takes the CUDA-core
+    kernels); fp32 only."""
+    require_cuda(A, B, row_alpha, E, row_beta)
+    if A.dtype != torch.float32 or B.dtype != torch.float32:
+        return None
+    lib = _lib.load()
+
+    def as3(t):
+        t = t if t.dim() == 3 else t.reshape(1, *t.shape[-2:]) if t.dim() == 2 else t.reshape(-1, *t.shape[-2:])
+        if t.stride(-1) != 1 or t.stride(-2) < t.shape[-1] or (t.shape[0] > 1 and t.stride(0) < t.shape[-2] * t.stride(-2)):
+            t = t.contiguous()
+        return t
+
+    A3, B3 = as3(A), as3(B)
+    M, K = (A3.shape[2], A3.shape[1]) if trans_a else (A3.shape[1], A3.shape[2])
+    Kb, N = (B3.shape[2], B3.shape[1]) if trans_b else (B3.shape[1], B3.shape[2])
+    if K != Kb:
+        raise RuntimeError(f"Size mismatch in gemm3x: {tuple(A.shape)} (trans={trans_a}) x {tuple(B.shape)} (trans={trans_b})")
+    nb = batch if batch is not None else max(A3.shape[0] * a_div, B3.shape[0] * b_div)
+    out_dtype = out_dtype or torch.float32
+    want_splits = int(lib.lob_gemm3x_splits(nb, M, N, K, int(splits)))
+    if out_dtype == torch.float64 and want_splits == 1:
+        want_splits = int(lib.lob_gemm3x_splits(nb, M, N, K, 2))
+        if want_splits == 1:
+            return None
+        splits = 2
+    D = torch.empty(nb, M, N, dtype=out_dtype, device=A.device)
+    ws_bytes = int(lib.lob_gemm3x_workspace_bytes(nb, M, N, K, int(splits)))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=A.device) if ws_bytes else None
+    ra = None if row_alpha is None else row_alpha.to(torch.float32).expand(nb, M).contiguous()
+    rb = None if row_beta is None else row_beta.to(torch.float32).expand(nb, M).contiguous()
+    E3 = None
+    if E is not None:
+        E3 = E.reshape(nb, M, N)
+        if E3.stride(-1) != 1:
+            E3 = E3.contiguous()
+    status = lib.lob_gemm3x(
+        nb, M, N, K, ptr(A3), 1 if trans_a else 0, A3.stride(1), A3.stride(0) if A3.shape[0] > 1 else 0, int(a_div),
+        ptr(B3), 0 if trans_b else 1, B3.stride(1), B3.stride(0) if B3.shape[0] > 1 else 0, int(b_div),
+        ptr(D), _lib._DT[out_dtype], N, M * N, float(alpha), ptr(ra), M, ptr(E3),
+        0 if E3 is None else E3.stride(1), 0 if E3 is None else E3.stride(0), ptr(rb), M, int(splits), ptr(ws), ws_bytes,
+        stream(A))
+    if status == _lib.UNSUPPORTED:
+        return None
+    check(status, "lob_gemm3x")
+    return D
+
+
 def matmul_nn(A: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
     """Y = A X for small-K products (Q t, L eps, U w).  A (*ba, M, K), X (*bx, K, C), batches broadcast."""
     require_cuda(A, X)
@@ -470,16 +525,84 @@ def tridiag_eigh_slq(t_mat: torch.Tensor, n: int, want_evals=False, want_evecs=F
 # ------------------------------------------------------------------------------------------------------------
 # structured matmuls
 # ------------------------------------------------------------------------------------------------------------
-def kron_matmul(factors: Sequence[torch.Tensor], X: torch.Tensor) -> torch.Tensor:
-    """(K1 (x) K2 (x) ...) X as one fused mode product per factor (kronecker_product_linear_operator.py:34-45)."""
-    require_cuda(X, *factors)
+def _kron_tensor_core_ok(factors, X) -> bool:
+    """The tcgen05 chain needs TMA-addressable views: fp32, square factors with sizes that are multiples of 4 (leading
+    dimensions of the factor and of every mode's (n_i x post) slab)."""
+    if X.dtype != torch.float32 or len(factors) < 2:
+        return False
+    sizes = [int(f.shape[-1]) for f in factors]
+    if any(f.shape[-2] != f.shape[-1] for f in factors) or any(n % 4 for n in sizes):
+        return False
+    return int(math.prod(sizes)) == X.shape[-2]
+
+
+def _kron_matmul_tc(factors, X, d):
+    """(K1 (x) ... (x) Km) X (+ d (.) X) as a chain of tensor-core GEMMs (csrc/gemm3x.cu) on column planes.
+
+    The vector block X (B, N, C) has C = 33 columns: a slab with a 33-element leading dimension is not TMA-addressable,
+    so the chain works on the transposed planes Xt (B, C, n1, ..., nm) (one transposing pass in, one out -- the same
+    kernels as the Toeplitz pad / unpad, with the + d (.) X of AddedDiag fused into the way out).  With pre = n1..n_{i-1}
+    and post = n_{i+1}..n_m, mode i is the batched GEMM  Y[b,c,p] (n_i x post) = K_i[b] X[b,c,p] (n_i x post) for i < m
+    and, for the last mode,  Y[b,c] (pre x n_m) = X[b,c] (pre x n_m) K_m[b]^T.  The index order never changes, so there
+    are no transposing copies between the modes (kronecker_product_linear_operator.py:34-45 has one per factor):
+    m + 2 passes over the vector in total, every product on the tensor cores."""
     lib = _lib.load()
+    batch_shape = torch.broadcast_shapes(X.shape[:-2], *[f.shape[:-2] for f in factors])
+    B = _numel(batch_shape)
+    N, C = X.shape[-2:]
+    Xf = _flat3(X.expand(*batch_shape, N, C))
+    fl = []
+    for f in factors:
+        n = f.shape[-1]
+        fl.append(f.reshape(1, n, n).contiguous() if _numel(f.shape[:-2]) == 1 else _flat3(f.expand(*batch_shape, n, n)))
+    sizes = [int(f.shape[-1]) for f in factors]
+    dd, d_bs, d_st = _diag_args(d, batch_shape, N)
+    Y = torch.empty(B, N, C, dtype=X.dtype, device=X.device)
+    # batch chunks keep every mode's GEMM batch (B * C * pre) inside the launch limit
+    max_pre = int(math.prod(sizes[:-2])) if len(sizes) > 2 else 1
+    bchunk = max(1, min(B, 65535 // (C * max_pre)))
+    for b0 in range(0, B, bchunk):
+        b1 = min(B, b0 + bchunk)
+        nb = b1 - b0
+        cur = torch.empty(nb, C, N, dtype=X.dtype, device=X.device)
+        check(lib.lob_toeplitz_pad(dt(X), nb, N, C, N, ptr(Xf[b0:b1]), ptr(cur), stream(X)), "lob_toeplitz_pad")
+        pre = 1
+        for i, n in enumerate(sizes):
+            post = N // (pre * n)
+            Ki = fl[i] if fl[i].shape[0] == 1 else fl[i][b0:b1]
+            shared = Ki.shape[0] == 1
+            if i < len(sizes) - 1:
+                nbatch = nb * C * pre
+                out = gemm3x(Ki, cur.reshape(nbatch, n, post), a_div=(nbatch if shared else C * pre), batch=nbatch)
+            else:
+                nbatch = nb * C
+                out = gemm3x(cur.reshape(nbatch, pre, n), Ki, trans_b=True, b_div=(nbatch if shared else C),
+                             batch=nbatch)
+            if out is None:
+                raise _lib.LobError("Kronecker tensor-core chain: operand not TMA-addressable")
+            cur = out
+            pre *= n
+        dd_c = dd if (dd is None or d_bs == 0) else dd[b0:b1]
+        check(
+            lib.lob_toeplitz_unpad(dt(X), nb, N, C, N, ptr(cur), 1.0, ptr(Xf[b0:b1]), ptr(dd_c), d_bs, d_st,
+                                   ptr(Y[b0:b1]), stream(X)),
+            "lob_toeplitz_unpad",
+        )
+    return Y.reshape(*batch_shape, N, C)
+
+
+def kron_matmul(factors: Sequence[torch.Tensor], X: torch.Tensor, d: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(K1 (x) K2 (x) ...) X (+ d (.) X)  (kronecker_product_linear_operator.py:34-45; added_diag_linear_operator.py
+    :72-76 for the fused diagonal).  fp32 operators with TMA-addressable factors run as a tensor-core GEMM chain
+    (``_kron_matmul_tc``); everything else (fp64, odd factor sizes) as one fused CUDA-core mode product per factor."""
+    require_cuda(X, d, *factors)
+    lib = _lib.load()
+    if _kron_tensor_core_ok(factors, X):
+        return _kron_matmul_tc(factors, X, d)
     batch_shape = torch.broadcast_shapes(X.shape[:-2], *[f.shape[:-2] for f in factors])
     B = _numel(batch_shape)
     Ntot, C = X.shape[-2:]
     cur = _flat3(X.expand(*batch_shape, Ntot, C))
-    if cur.data_ptr() == X.data_ptr():
-        pass  # never written: the first mode product writes to a fresh buffer
     for f in factors:
         n = f.shape[-1]
         if f.shape[-2] != n:
@@ -493,7 +616,10 @@ def kron_matmul(factors: Sequence[torch.Tensor], X: torch.Tensor) -> torch.Tenso
         check(lib.lob_kron_mode_matmul(dt(X), B, n, Q, C, ptr(ff), k_bs, ptr(cur), ptr(out), stream(X)),
               "lob_kron_mode_matmul")
         cur = out
-    return cur.reshape(*batch_shape, Ntot, C)
+    cur = cur.reshape(*batch_shape, Ntot, C)
+    if d is not None:
+        cur = cur.add_(scale_rows(X.expand(*batch_shape, Ntot, C), d, "mul"))
+    return cur
 
 
 def _next_pow2(n: int) -> int:

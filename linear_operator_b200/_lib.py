@@ -145,6 +145,14 @@ _SIGS = {
     ),
     "lob_cap_solve_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int64]),
     "lob_cap_solve": (ctypes.c_int, [c_int32, c_int64, c_int32, c_int64, _P, c_int64, _P, _P, _P, _P, _P]),
+    "lob_gemm3x_splits": (c_int32, [c_int64, c_int64, c_int64, c_int64, c_int32]),
+    "lob_gemm3x_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int32]),
+    "lob_gemm3x": (
+        ctypes.c_int,
+        [c_int64, c_int64, c_int64, c_int64, _P, c_int32, c_int64, c_int64, c_int64, _P, c_int32, c_int64, c_int64,
+         c_int64, _P, c_int32, c_int64, c_int64, c_double, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int32, _P,
+         c_size_t, _P],
+    ),
     "lob_bilinear_dense": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int32, _P]),
     "lob_bilinear_diag": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "lob_tri_inverse": (ctypes.c_int, [c_int32, c_int64, c_int32, _P, c_int64, c_int64, _P, _P]),
@@ -178,6 +186,9 @@ def load():
 
 def launch_count() -> int:
     return int(load().lob_launch_count())
+
+
+UNSUPPORTED = -3
 
 
 def check(status: int, what: str):

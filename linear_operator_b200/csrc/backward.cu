@@ -16,16 +16,17 @@
 
 namespace lob {
 
-// CTA tile (16*TM) x (16*TN), 256 threads, thread tile TM x TN; operands staged c-major in shared memory
-template <typename T, int TM, int TN>
+// CTA tile (16*TM) x (16*TN), 256 threads, thread tile TM x TN; operands staged c-major in shared memory, CK columns
+// per stage (CK >= C for the path's 33-column blocks: one load phase, one barrier pair per tile).
+template <typename T, int TM, int TN, int CK>
 __global__ void __launch_bounds__(256)
 k_bilinear_dense(int64_t N, int64_t M, int C, const T* __restrict__ Lf, const T* __restrict__ Rt,
                  const T* __restrict__ w, T* __restrict__ G, int accumulate) {
   constexpr int BM = 16 * TM, BN = 16 * TN;
   constexpr int LDL = BM + 4, LDR = BN + 4;
-  constexpr int CK = 16;  // columns per stage
-  __shared__ __align__(16) T Ls[CK * LDL];
-  __shared__ __align__(16) T Rs[CK * LDR];
+  extern __shared__ __align__(16) unsigned char bl_smem[];
+  T* Ls = reinterpret_cast<T*>(bl_smem);  // [CK][LDL]
+  T* Rs = Ls + CK * LDL;                  // [CK][LDR]
   const int64_t b = blockIdx.z;
   const int64_t i0 = (int64_t)blockIdx.y * BM, j0 = (int64_t)blockIdx.x * BN;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -41,21 +42,33 @@ k_bilinear_dense(int64_t N, int64_t M, int C, const T* __restrict__ Lf, const T*
   for (int c0 = 0; c0 < C; c0 += CK) {
     const int cw = min(CK, C - c0);
     __syncthreads();
-    // rows i0..i0+BM of L are one contiguous chunk of BM*C elements: read coalesced, scatter c-major
-    for (int e = tid; e < BM * cw; e += 256) {
-      const int i = e / cw, c = e - i * cw;
-      T v = (T)0;
-      if (i0 + i < N) {
-        v = Lb[(i0 + i) * C + c0 + c];
-        if (wb) v *= wb[c0 + c];
+    // rows i0..i0+BM of L are BM runs of cw contiguous elements (one contiguous chunk when cw == C): read them in
+    // element order, scatter c-major; (i, c) advance incrementally -- no division in the loop
+    {
+      const int di = 256 / cw, dc = 256 - di * cw;
+      int i = tid / cw, c = tid - i * cw;
+      for (; i < BM; ) {
+        T v = (T)0;
+        if (i0 + i < N) {
+          v = Lb[(i0 + i) * C + c0 + c];
+          if (wb) v *= wb[c0 + c];
+        }
+        Ls[c * LDL + i] = v;
+        i += di;
+        c += dc;
+        if (c >= cw) { c -= cw; ++i; }
       }
-      Ls[c * LDL + i] = v;
-    }
-    for (int e = tid; e < BN * cw; e += 256) {
-      const int j = e / cw, c = e - j * cw;
-      Rs[c * LDR + j] = (j0 + j < M) ? Rb[(j0 + j) * C + c0 + c] : (T)0;
+      i = tid / cw;
+      c = tid - i * cw;
+      for (; i < BN; ) {
+        Rs[c * LDR + i] = (j0 + i < M) ? Rb[(j0 + i) * C + c0 + c] : (T)0;
+        i += di;
+        c += dc;
+        if (c >= cw) { c -= cw; ++i; }
+      }
     }
     __syncthreads();
+#pragma unroll 4
     for (int c = 0; c < cw; ++c) {
       T a[TM], q[TN];
 #pragma unroll
@@ -69,17 +82,42 @@ k_bilinear_dense(int64_t N, int64_t M, int C, const T* __restrict__ Lf, const T*
     }
   }
   T* Gb = G + b * N * M;
+  const int64_t jb = j0 + tx * TN;
+  // 16-byte stores when the row segment is aligned and complete (fp32: 2 x float4 per row, fp64: 2 x double2)
+  constexpr int VEC = 16 / sizeof(T);
+  const bool vec = (jb + TN <= M) && ((M % VEC) == 0) && ((reinterpret_cast<uintptr_t>(Gb) & 15) == 0) && (TN % VEC) == 0;
 #pragma unroll
   for (int u = 0; u < TM; ++u) {
     const int64_t i = i0 + ty * TM + u;
     if (i >= N) continue;
+    T* row = Gb + i * M + jb;
+    if (vec) {
 #pragma unroll
-    for (int v = 0; v < TN; ++v) {
-      const int64_t j = j0 + tx * TN + v;
-      if (j < M) {
-        T r = acc[u][v];
-        if (accumulate) r += Gb[i * M + j];
-        Gb[i * M + j] = r;
+      for (int v = 0; v < TN; v += VEC) {
+        if constexpr (sizeof(T) == 4) {
+          float4 o = make_float4(acc[u][v], acc[u][v + 1], acc[u][v + 2], acc[u][v + 3]);
+          if (accumulate) {
+            const float4 g = *reinterpret_cast<const float4*>(row + v);
+            o.x += g.x; o.y += g.y; o.z += g.z; o.w += g.w;
+          }
+          *reinterpret_cast<float4*>(row + v) = o;
+        } else {
+          double2 o = make_double2(acc[u][v], acc[u][v + 1]);
+          if (accumulate) {
+            const double2 g = *reinterpret_cast<const double2*>(row + v);
+            o.x += g.x; o.y += g.y;
+          }
+          *reinterpret_cast<double2*>(row + v) = o;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < TN; ++v) {
+        if (jb + v < M) {
+          T r = acc[u][v];
+          if (accumulate) r += row[v];
+          row[v] = r;
+        }
       }
     }
   }
@@ -168,12 +206,20 @@ extern "C" int lob_bilinear_dense(int32_t dtype, int64_t B, int64_t N, int64_t M
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == LOB_F32) {
     dim3 grid((unsigned)cdiv(M, 128), (unsigned)cdiv(N, 128), (unsigned)B);
-    k_bilinear_dense<float, 8, 8><<<grid, 256, 0, st>>>(N, M, (int)C, (const float*)left, (const float*)right,
-                                                        (const float*)w, (float*)out, accumulate);
+    constexpr int CK = 48;
+    const size_t sm = (size_t)CK * (132 + 132) * sizeof(float);
+    auto kern = k_bilinear_dense<float, 8, 8, CK>;
+    LOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<grid, 256, sm, st>>>(N, M, (int)C, (const float*)left, (const float*)right, (const float*)w, (float*)out,
+                                accumulate);
   } else if (dtype == LOB_F64) {
     dim3 grid((unsigned)cdiv(M, 64), (unsigned)cdiv(N, 64), (unsigned)B);
-    k_bilinear_dense<double, 4, 4><<<grid, 256, 0, st>>>(N, M, (int)C, (const double*)left, (const double*)right,
-                                                         (const double*)w, (double*)out, accumulate);
+    constexpr int CK = 48;
+    const size_t sm = (size_t)CK * (68 + 68) * sizeof(double);
+    auto kern = k_bilinear_dense<double, 4, 4, CK>;
+    LOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<grid, 256, sm, st>>>(N, M, (int)C, (const double*)left, (const double*)right, (const double*)w,
+                                (double*)out, accumulate);
   } else {
     return fail(LOB_ERR_ARG, "dtype must be LOB_F32 or LOB_F64");
   }

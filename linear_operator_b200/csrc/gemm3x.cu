@@ -1,0 +1,430 @@
+// gemm3x.cu -- batched fp32-accurate GEMM on the 5th-generation tensor cores:  D = alpha * A B (+ epilogue), 3xTF32.
+//
+// Serves the products of the path that are plain GEMMs rather than operator streams:
+//   * the two tall products of the low-rank Woodbury solve (low_rank_root_added_diag_linear_operator.py:62-87) with the
+//     batch as the GEMM row dimension:  W = R U  (split-K over N = 10^7)  and  x = (R - w U^T) / sigma  (fused epilogue);
+//   * the mode products of KroneckerProductLinearOperator._matmul (kronecker_product_linear_operator.py:34-45);
+//   * Q = L R^-1 of the preconditioner build (added_diag_linear_operator.py:164-166).
+//
+// Operands are fp32 in global memory in either major-ness (UMMA "K-major": the contraction index is contiguous;
+// "MN-major": the row / column index is contiguous -- a row-major (K, N) matrix is an MN-major B operand), so no
+// caller ever transposes.  Each CTA computes one 128 x 128 tile of D over one K range:
+//   warp 0       TMA producer: A and B tiles (128 x 32 fp32, SWIZZLE_128B) into a 3-stage ring
+//   warps 8-15   converters: lo = x - trunc_tf32(x) for both tiles, same offsets, smem -> smem (the tensor core reads the
+//                raw fp32 words as tf32, i.e. truncated: hi costs nothing)
+//   warp 1       MMA issuer: per 8-wide k step  D += A_hi B_hi,  Dc += A_hi B_lo + A_lo B_hi   (two fp32 accumulators in
+//                TMEM: the main one takes a single truncating add per k step, the corrections are added in the epilogue)
+//   warps 4-7    epilogue: tcgen05.ld, row scalings, + E, vectorised stores; split-K tiles store raw partial sums that
+//                k_g3_reduce adds in a fixed order (double accumulation, deterministic)
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "tcgen05_util.cuh"
+
+namespace lob {
+
+constexpr int G3_BM = 128, G3_BN = 128, G3_BK = 32;
+constexpr int G3_THREADS = 512, G3_CONV_THREADS = 256;
+constexpr int G3_TILE_BYTES = 128 * G3_BK * 4;      // 16 KB, either major-ness
+constexpr int G3_STAGE_BYTES = 4 * G3_TILE_BYTES;   // A | B | A_lo | B_lo
+constexpr int G3_STAGES = 3;
+constexpr size_t G3_SMEM = 1024 + (size_t)G3_STAGES * G3_STAGE_BYTES + 256;
+
+struct G3Params {
+  float* D;
+  int64_t ldd, d_bs;
+  const float* E;
+  int64_t lde, e_bs;
+  const float* row_alpha;  // out = row_alpha[batch * ra_bs + m] * acc   (NULL: alpha)
+  int64_t ra_bs;
+  const float* row_beta;   //     + row_beta[batch * rb_bs + m] * E[m][n] (NULL: 1)
+  int64_t rb_bs;
+  float alpha;
+  float* partial;  // (batch, splits, M, N) raw partial sums when splits > 1
+  int64_t M, N, K;
+  int tiles_n;
+  int splits;
+  int64_t kps;           // K range per split (multiple of G3_BK)
+  int64_t a_div, b_div;  // operand batch index = batch / div (shared / grouped operands)
+  int a_mn, b_mn;
+};
+
+// MN-major operand tile: 4 regions of [32 k rows][32 floats = 128 B].  For 32-bit operands the tensor core accepts ONE
+// MN-major shared-memory layout: 128-byte rows swizzled in 32-byte chunks (UMMA layout type 1, "SWIZZLE_128B_BASE32B";
+// TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), whose atom is 4 k rows x 128 B.  Regions (32 further rows / columns of
+// the operand) are 4096 B apart (leading byte offset), 4-row k atoms 512 B apart (stride byte offset).
+__device__ __forceinline__ uint64_t g3_mn_desc(uint32_t smem_addr) {
+  uint64_t desc = 0;
+  desc |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  desc |= (uint64_t)(4096 >> 4) << 16;
+  desc |= (uint64_t)(512 >> 4) << 32;
+  desc |= (uint64_t)1 << 46;
+  desc |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return desc;
+}
+
+__device__ __forceinline__ uint64_t g3_desc(uint32_t tile_addr, int mn, int kstep) {
+  if (mn) return g3_mn_desc(tile_addr + kstep * 1024);
+  return ds::make_kmajor_desc<32>(tile_addr) + (uint64_t)((kstep * 32) >> 4);
+}
+
+__global__ void __launch_bounds__(G3_THREADS, 1)
+k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, G3Params p) {
+  using namespace ds;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G3_STAGES * G3_STAGE_BYTES);
+  uint64_t* full = bars;                   // TMA -> converters, MMA
+  uint64_t* empty = full + G3_STAGES;      // MMA (commit) -> TMA
+  uint64_t* lo_full = empty + G3_STAGES;   // converters -> MMA
+  uint64_t* acc_full = lo_full + G3_STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+  const int split = blockIdx.y;
+  const int64_t batch = blockIdx.z;
+  const int64_t m0 = (int64_t)tm * G3_BM, n0 = (int64_t)tn * G3_BN;
+  const int64_t k_begin = (int64_t)split * p.kps;
+  const int64_t k_end = min(p.K, k_begin + p.kps);
+  const int nkb = (int)((k_end - k_begin + G3_BK - 1) / G3_BK);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int i = 0; i < G3_STAGES; ++i) {
+      mbar_init(smem_u32(&full[i]), 1);
+      mbar_init(smem_u32(&empty[i]), 1);
+      mbar_init(smem_u32(&lo_full[i]), G3_CONV_THREADS / 32);
+    }
+    mbar_init(smem_u32(acc_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_holder))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint64_t pol;
+      asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+      const int ab = (int)(batch / p.a_div), bb = (int)(batch / p.b_div);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+        const uint32_t bar = smem_u32(&full[s]);
+        mbar_arrive_expect_tx(bar, 2 * G3_TILE_BYTES);
+        const uint32_t dst = smem_u32(smem + s * G3_STAGE_BYTES);
+        const int k0 = (int)(k_begin + (int64_t)kb * G3_BK);
+        if (!p.a_mn) {
+          tma_load_3d(dst, &tmA, bar, k0, (int)m0, ab, pol);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * 4096, &tmA, bar, (int)m0 + 32 * j, k0, ab, pol);
+        }
+        if (!p.b_mn) {
+          tma_load_3d(dst + G3_TILE_BYTES, &tmB, bar, k0, (int)n0, bb, pol);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            tma_load_3d(dst + G3_TILE_BYTES + j * 4096, &tmB, bar, (int)n0 + 32 * j, k0, bb, pol);
+        }
+        if (++s == G3_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_tf32(G3_BM, G3_BN) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                           ((uint32_t)(p.b_mn ? 1 : 0) << 16);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(smem_u32(&full[s]), ph);
+      mbar_wait(smem_u32(&lo_full[s]), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem + s * G3_STAGE_BYTES);
+        const uint32_t b_addr = a_addr + G3_TILE_BYTES;
+        const uint32_t al_addr = a_addr + 2 * G3_TILE_BYTES, bl_addr = a_addr + 3 * G3_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < G3_BK / 8; ++k) {
+          const uint64_t a_hi = g3_desc(a_addr, p.a_mn, k), b_hi = g3_desc(b_addr, p.b_mn, k);
+          const uint64_t a_lo = g3_desc(al_addr, p.a_mn, k), b_lo = g3_desc(bl_addr, p.b_mn, k);
+          // the small correction terms go to their own accumulator (columns 128..255): the main accumulator then takes
+          // one truncating fp32 add per k step instead of three, and the corrections are added once, in the epilogue
+          umma_tf32_ss(tmem_base, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
+          umma_tf32_ss(tmem_base + G3_BN, a_hi, b_lo, idesc, (kb | k) ? 1u : 0u);
+          umma_tf32_ss(tmem_base + G3_BN, a_lo, b_hi, idesc, 1u);
+        }
+        umma_commit(smem_u32(&empty[s]));
+        if (kb == nkb - 1) umma_commit(smem_u32(acc_full));
+      }
+      __syncwarp();
+      if (++s == G3_STAGES) { s = 0; ph ^= 1; }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue: thread = output row =====================
+    const int q = warp & 3;
+    const int64_t m = m0 + q * 32 + lane;
+    mbar_wait(smem_u32(acc_full), 0);
+    __syncwarp();
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool row_ok = m < p.M;
+    float* dst;
+    int64_t ld;
+    float ra = p.alpha, rb = 1.f;
+    const float* erow = nullptr;
+    if (p.splits > 1) {
+      dst = p.partial + ((batch * p.splits + split) * p.M + (row_ok ? m : 0)) * p.N;
+      ld = p.N;
+      ra = 1.f;
+    } else {
+      dst = p.D + batch * p.d_bs + (row_ok ? m : 0) * p.ldd;
+      ld = p.ldd;
+      if (row_ok) {
+        if (p.row_alpha) ra = p.row_alpha[batch * p.ra_bs + m];
+        if (p.E) {
+          erow = p.E + batch * p.e_bs + m * p.lde;
+          if (p.row_beta) rb = p.row_beta[batch * p.rb_bs + m];
+        }
+      }
+    }
+    (void)ld;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                        (erow == nullptr || (reinterpret_cast<uintptr_t>(erow) & 15) == 0);
+#pragma unroll 1
+    for (int chunk = 0; chunk < G3_BN / 32; ++chunk) {
+      const int64_t nb = n0 + chunk * 32;
+      if (nb >= p.N) break;  // warp-uniform
+      uint32_t r[32], rc[32];
+      DS_LD32(taddr + chunk * 32, r);
+      DS_LD32(taddr + G3_BN + chunk * 32, rc);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!row_ok) continue;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(rc[i]));
+      if (vec_ok && nb + 32 <= p.N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 v = make_float4(__uint_as_float(r[i]) * ra, __uint_as_float(r[i + 1]) * ra,
+                                 __uint_as_float(r[i + 2]) * ra, __uint_as_float(r[i + 3]) * ra);
+          if (erow) {
+            const float4 e = *reinterpret_cast<const float4*>(erow + nb + i);
+            v.x = fmaf(rb, e.x, v.x); v.y = fmaf(rb, e.y, v.y); v.z = fmaf(rb, e.z, v.z); v.w = fmaf(rb, e.w, v.w);
+          }
+          *reinterpret_cast<float4*>(dst + nb + i) = v;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (nb + i < p.N) {
+            float v = __uint_as_float(r[i]) * ra;
+            if (erow) v = fmaf(rb, erow[nb + i], v);
+            dst[nb + i] = v;
+          }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== converters: lo = x - trunc_tf32(x), both operand tiles =====================
+    const int ct = threadIdx.x - (G3_THREADS - G3_CONV_THREADS);
+    constexpr int NV = 2 * G3_TILE_BYTES / 16 / G3_CONV_THREADS;  // 8 x 16 bytes per thread per k block
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(smem_u32(&full[s]), ph);
+      const uint4* src = reinterpret_cast<const uint4*>(smem + s * G3_STAGE_BYTES) + ct;
+      uint4* dstv = reinterpret_cast<uint4*>(smem + s * G3_STAGE_BYTES + 2 * G3_TILE_BYTES) + ct;
+      uint4 v[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = src[i * G3_CONV_THREADS];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        uint4 o;
+        o.x = __float_as_uint(__uint_as_float(v[i].x) - __uint_as_float(v[i].x & 0xFFFFE000u));
+        o.y = __float_as_uint(__uint_as_float(v[i].y) - __uint_as_float(v[i].y & 0xFFFFE000u));
+        o.z = __float_as_uint(__uint_as_float(v[i].z) - __uint_as_float(v[i].z & 0xFFFFE000u));
+        o.w = __float_as_uint(__uint_as_float(v[i].w) - __uint_as_float(v[i].w & 0xFFFFE000u));
+        dstv[i * G3_CONV_THREADS] = o;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&lo_full[s]));
+      if (++s == G3_STAGES) { s = 0; ph ^= 1; }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// out[b][m][n] = ra * sum_s partial[b][s][m][n]  (+ rb * E), splits added in a fixed order in double
+template <typename TO>
+__global__ void __launch_bounds__(256)
+k_g3_reduce(G3Params p, TO* __restrict__ out) {
+  const int64_t total = p.M * p.N;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t batch = blockIdx.y;
+  if (idx >= total) return;
+  const int64_t m = idx / p.N, n = idx - m * p.N;
+  const float* src = p.partial + batch * p.splits * total + idx;
+  double s = 0.0;
+  for (int i = 0; i < p.splits; ++i) s += (double)src[(int64_t)i * total];
+  double ra = p.row_alpha ? (double)p.row_alpha[batch * p.ra_bs + m] : (double)p.alpha;
+  double v = s * ra;
+  if (p.E) v += (p.row_beta ? (double)p.row_beta[batch * p.rb_bs + m] : 1.0) * (double)p.E[batch * p.e_bs + m * p.lde + n];
+  out[batch * p.d_bs + m * p.ldd + n] = (TO)v;
+}
+
+typedef CUresult (*PFN_encodeTiled_g3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled_g3 g3_encode_fn() {
+  static PFN_encodeTiled_g3 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled_g3)ptr;
+  }
+  return fn;
+}
+
+// operand (rows x K) with `rows` = M or N.  K-major: element (r, k) at ptr[r * ld + k]; MN-major: ptr[k * ld + r].
+static bool g3_make_map(CUtensorMap* tm, const float* ptr, int mn, int64_t rows, int64_t K, int64_t ld, int64_t bs,
+                        int64_t nbatch) {
+  PFN_encodeTiled_g3 enc = g3_encode_fn();
+  if (!enc) return false;
+  if ((ld % 4) != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return false;
+  if (nbatch > 1 && (bs % 4) != 0) return false;
+  if (rows >= (1LL << 31) || K >= (1LL << 31) || nbatch >= (1LL << 31)) return false;
+  const int64_t inner = mn ? rows : K, outer = mn ? K : rows;
+  const int64_t bstride = (nbatch > 1) ? bs : outer * ld;
+  if ((uint64_t)ld * 4 >= (1ULL << 40) || (uint64_t)bstride * 4 >= (1ULL << 40)) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)nbatch};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, (cuuint64_t)bstride * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)(mn ? G3_BK : 128), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static int g3_pick_splits(int64_t batch, int64_t M, int64_t N, int64_t K, int requested) {
+  const int64_t tiles = batch * cdiv(M, G3_BM) * cdiv(N, G3_BN);
+  const int64_t max_splits = std::max<int64_t>(1, cdiv(K, 8 * G3_BK));  // at least 8 k blocks per split
+  int64_t s = requested;
+  if (s <= 0) {
+    s = 1;
+    if (tiles < kNumSMs) s = cdiv(2 * kNumSMs, tiles);
+  }
+  if (s > max_splits) s = max_splits;
+  if (s > 1024) s = 1024;
+  if (s < 1) s = 1;
+  // every split must own at least one k block
+  int64_t kps = cdiv(cdiv(K, s), G3_BK) * G3_BK;
+  s = cdiv(K, kps);
+  return (int)s;
+}
+
+}  // namespace lob
+
+using namespace lob;
+
+extern "C" int32_t lob_gemm3x_splits(int64_t batch, int64_t M, int64_t N, int64_t K, int32_t requested) {
+  if (batch <= 0 || M <= 0 || N <= 0 || K <= 0) return 1;
+  return g3_pick_splits(batch, M, N, K, requested);
+}
+
+extern "C" size_t lob_gemm3x_workspace_bytes(int64_t batch, int64_t M, int64_t N, int64_t K, int32_t requested_splits) {
+  if (batch <= 0 || M <= 0 || N <= 0 || K <= 0) return 0;
+  const int s = g3_pick_splits(batch, M, N, K, requested_splits);
+  return s > 1 ? (size_t)batch * s * M * N * sizeof(float) : 0;
+}
+
+extern "C" int lob_gemm3x(int64_t batch, int64_t M, int64_t N, int64_t K, const void* A, int32_t a_mn, int64_t lda,
+                          int64_t a_batch_stride, int64_t a_batch_div, const void* B, int32_t b_mn, int64_t ldb,
+                          int64_t b_batch_stride, int64_t b_batch_div, void* D, int32_t d_dtype, int64_t ldd,
+                          int64_t d_batch_stride, double alpha, const void* row_alpha, int64_t row_alpha_batch_stride,
+                          const void* E, int64_t lde, int64_t e_batch_stride, const void* row_beta,
+                          int64_t row_beta_batch_stride, int32_t requested_splits, void* ws, size_t ws_bytes,
+                          void* stream) {
+  LOB_REQUIRE(batch > 0 && M > 0 && N > 0 && K > 0, "lob_gemm3x: sizes must be positive");
+  LOB_REQUIRE(A && B && D, "lob_gemm3x: NULL pointer");
+  LOB_REQUIRE(a_batch_div >= 1 && b_batch_div >= 1, "lob_gemm3x: batch divisors must be >= 1");
+  LOB_REQUIRE(batch <= 65535, "lob_gemm3x: batch > 65535 not supported");
+  LOB_REQUIRE(d_dtype == LOB_F32 || d_dtype == LOB_F64, "lob_gemm3x: output dtype must be LOB_F32 or LOB_F64");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int splits = g3_pick_splits(batch, M, N, K, requested_splits);
+  if (d_dtype == LOB_F64 && splits == 1) return fail(LOB_ERR_UNSUPPORTED, "lob_gemm3x: fp64 output needs the split-K path");
+  const int64_t tiles_m = cdiv(M, G3_BM), tiles_n = cdiv(N, G3_BN);
+  if (tiles_m * tiles_n >= (1LL << 31) || splits > 65535) return fail(LOB_ERR_UNSUPPORTED, "lob_gemm3x: grid too large");
+  CUtensorMap tmA, tmB;
+  if (!g3_make_map(&tmA, (const float*)A, a_mn, M, K, lda, a_batch_stride, cdiv(batch, a_batch_div)) ||
+      !g3_make_map(&tmB, (const float*)B, b_mn, N, K, ldb, b_batch_stride, cdiv(batch, b_batch_div)))
+    return fail(LOB_ERR_UNSUPPORTED, "lob_gemm3x: operand layout not TMA-addressable (16-byte alignment of base / strides)");
+  G3Params p;
+  p.D = (float*)D;
+  p.ldd = ldd;
+  p.d_bs = d_batch_stride;
+  p.E = (const float*)E;
+  p.lde = lde;
+  p.e_bs = e_batch_stride;
+  p.row_alpha = (const float*)row_alpha;
+  p.ra_bs = row_alpha_batch_stride;
+  p.row_beta = (const float*)row_beta;
+  p.rb_bs = row_beta_batch_stride;
+  p.alpha = (float)alpha;
+  p.partial = nullptr;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.tiles_n = (int)tiles_n;
+  p.splits = splits;
+  p.kps = cdiv(cdiv(K, splits), G3_BK) * G3_BK;
+  p.a_div = a_batch_div;
+  p.b_div = b_batch_div;
+  p.a_mn = a_mn ? 1 : 0;
+  p.b_mn = b_mn ? 1 : 0;
+  if (splits > 1) {
+    const size_t need = (size_t)batch * splits * M * N * sizeof(float);
+    LOB_REQUIRE(ws && ws_bytes >= need, "lob_gemm3x: workspace too small for the split-K partial sums");
+    p.partial = (float*)ws;
+  }
+  LOB_CUDA(cudaFuncSetAttribute(k_gemm3x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G3_SMEM));
+  dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)splits, (unsigned)batch);
+  k_gemm3x<<<grid, G3_THREADS, G3_SMEM, st>>>(tmA, tmB, p);
+  LOB_TRY(check_launch("k_gemm3x"));
+  if (splits > 1) {
+    dim3 rgrid((unsigned)cdiv(M * N, 256), (unsigned)batch);
+    if (d_dtype == LOB_F64)
+      k_g3_reduce<double><<<rgrid, 256, 0, st>>>(p, (double*)D);
+    else
+      k_g3_reduce<float><<<rgrid, 256, 0, st>>>(p, (float*)D);
+    LOB_TRY(check_launch("k_g3_reduce"));
+  }
+  return LOB_OK;
+}

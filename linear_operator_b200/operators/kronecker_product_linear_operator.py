@@ -40,6 +40,10 @@ class KroneckerProductLinearOperator(LinearOperator):
         res = _kernels.kron_matmul(self._factor_tensors(), rhs)
         return res.squeeze(-1) if squeeze else res
 
+    def _matmul_add_diag(self, rhs, diag):
+        """K X + d (.) X with the diagonal folded into the chain's last pass (AddedDiagLinearOperator._matmul)."""
+        return _kernels.kron_matmul(self._factor_tensors(), rhs, d=diag)
+
     def _transpose_nonbatch(self):
         return self.__class__(*(op._transpose_nonbatch() for op in self.linear_ops))
 

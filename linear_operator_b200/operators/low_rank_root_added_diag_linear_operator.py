@@ -30,7 +30,7 @@ class LowRankRootAddedDiagLinearOperator(AddedDiagLinearOperator):
         element.  The reference would materialise D^-1 U as (*batch, N, r) (low_rank_root_added_diag_...py:44 through
         diag_linear_operator.py:211-212: 40 TB at the config's sizes); here U^T D^-1 U = (U^T U) / sigma_b, the r x r
         Gram matrix is computed once, and the two tall products become plain (batch x N) x (N x r) GEMMs that read U
-        once for the whole batch."""
+        once for the whole batch -- on the tensor cores through ``_kernels.gemm3x``."""
         return (self._shared_root() is not None and isinstance(self._diag_tensor, ConstantDiagLinearOperator)
                 and len(self.batch_shape) > 0)
 
@@ -71,18 +71,31 @@ class LowRankRootAddedDiagLinearOperator(AddedDiagLinearOperator):
         U = self._linear_op._root_tensor()
         d = self._diag_tensor._diag
         if self._shared_root_constant_diag() and rhs.shape[-1] == 1 and rhs.shape[:-2] == self.batch_shape:
-            # x = (b - U (I + U^T U / s)^-1 U^T b / s) / s with the batch as the GEMM's row dimension.  The two products
-            # are plain dense GEMMs on contiguous operands (cuBLAS through torch.matmul), U is read once per product.
+            # x = (b - U (I + U^T U / s)^-1 U^T b / s) / s with the BATCH as the GEMM row dimension: U is read once per
+            # product for the whole batch.  Both tall products run on the tensor cores (csrc/gemm3x.cu, 3xTF32):
+            #   W = R U / s      (B x N) (N x r), split-K over N, 1/s folded into the reduction
+            #   x = (R - w U^T)/s (B x r) (r x N), the subtraction and the 1/s fused into the epilogue
             U = self._shared_root()
             _kernels.require_cuda(rhs, U)
             n, k = U.shape
             sig = self._sigma()
+            inv_sig = sig.reciprocal()
             R = rhs.reshape(-1, n)  # (B, N)
-            w = (torch.matmul(R, U) / sig.unsqueeze(-1)).unsqueeze(-1)  # U^T D^-1 b, (B, k, 1)
-            w, _, _ = _kernels.cap_solve(self._gram().reshape(-1, k, k), w)
-            S = torch.matmul(w.squeeze(-1), U.mT)  # (B, N) = (U w)^T
-            torch.sub(R, S, out=S)
-            return _kernels.scale_rows(S.reshape(*self.batch_shape, n, 1), d, "div")
+            w = _kernels.gemm3x(R.unsqueeze(0), U.unsqueeze(0), row_alpha=inv_sig.unsqueeze(0))  # U^T D^-1 b
+            if w is None:  # fp64 / unaligned: CUDA-core kernels
+                w = _kernels.tn_matmul(U.unsqueeze(0), R.mT.unsqueeze(0)).reshape(k, -1).mT * inv_sig.unsqueeze(-1)
+            else:
+                w = w[0]
+            w, _, _ = _kernels.cap_solve(self._gram().reshape(-1, k, k), w.unsqueeze(-1))
+            w = w.squeeze(-1)  # (B, k)
+            x = _kernels.gemm3x(w.unsqueeze(0), U.unsqueeze(0), trans_b=True, row_alpha=(-inv_sig).unsqueeze(0),
+                                E=R.unsqueeze(0), row_beta=inv_sig.unsqueeze(0))
+            if x is None:
+                S = _kernels.matmul_nn(U.unsqueeze(0), w.mT.unsqueeze(0))[0].mT  # (B, N) = (U w^T)^T
+                x = (R - S) * inv_sig.unsqueeze(-1)
+            else:
+                x = x[0]
+            return x.reshape(*self.batch_shape, n, 1)
         dinv_b = _kernels.scale_rows(rhs, d, "div")  # D^-1 b
         w = _kernels.tn_matmul(U, dinv_b)  # U^T D^-1 b
         w, _, _ = _kernels.cap_solve(self._gram(), w)  # (I + U^T D^-1 U)^-1 .
