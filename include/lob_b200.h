@@ -284,7 +284,9 @@ int lob_lanczos_step(int32_t dtype, int32_t mode, int64_t B, int64_t N, int64_t 
  * A is (M x K): a_mn == 0: element (m,k) at A[m*lda + k] ("K-major"), a_mn == 1: A[k*lda + m] ("MN-major").
  * B is (K x N): b_mn == 1: element (k,n) at B[k*ldb + n] (row-major K x N), b_mn == 0: B[n*ldb + k].
  * Epilogue: D[m][n] = ra(m) * acc + rb(m) * E[m][n] with ra(m) = row_alpha ? row_alpha[b*stride + m] : alpha and
- * rb(m) = row_beta ? row_beta[b*stride + m] : 1 (E NULL: no second term).  Split-K (requested_splits: 0 = automatic,
+ * rb(m) = row_beta ? row_beta[b*stride + m] : 1 (E NULL: no second term).  d_trans != 0 stores the TRANSPOSE: element
+ * (m,n) at D[n*ldd + m], E read likewise, and the two factor vectors are then indexed by n -- pick the operand roles so
+ * that the memory-contiguous index of the result is m (the tensor core's lane index): every store is a full line.  Split-K (requested_splits: 0 = automatic,
  * lob_gemm3x_splits() tells what will be used) needs ws = lob_gemm3x_workspace_bytes(); d_dtype LOB_F64 is available on
  * the split-K path (the reduction runs in double).  fp32 operands only; leading dimensions and batch strides must be
  * multiples of 4 elements and bases 16-byte aligned (TMA) -- otherwise LOB_ERR_UNSUPPORTED and the caller uses
@@ -297,7 +299,7 @@ int lob_gemm3x(int64_t batch, int64_t M, int64_t N, int64_t K, const void* A, in
                int64_t b_batch_stride, int64_t b_batch_div, void* D, int32_t d_dtype, int64_t ldd,
                int64_t d_batch_stride, double alpha, const void* row_alpha, int64_t row_alpha_batch_stride,
                const void* E, int64_t lde, int64_t e_batch_stride, const void* row_beta, int64_t row_beta_batch_stride,
-               int32_t requested_splits, void* ws, size_t ws_bytes, void* stream);
+               int32_t d_trans, int32_t requested_splits, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Backward pass (functions/_inv_quad_logdet.py:163-226, _solve.py:70-131, _inv_quad.py:63-93,

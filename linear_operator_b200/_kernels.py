@@ -110,11 +110,14 @@ def dense_matmul(A: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = N
 def gemm3x(A: torch.Tensor, B: torch.Tensor, trans_a: bool = False, trans_b: bool = False, alpha: float = 1.0,
            row_alpha: Optional[torch.Tensor] = None, E: Optional[torch.Tensor] = None,
            row_beta: Optional[torch.Tensor] = None, splits: int = 0, out_dtype: Optional[torch.dtype] = None,
-           a_div: int = 1, b_div: int = 1, batch: Optional[int] = None) -> Optional[torch.Tensor]:
+           a_div: int = 1, b_div: int = 1, batch: Optional[int] = None,
+           store_transposed: bool = False) -> Optional[torch.Tensor]:
     """D[b] = ra * op(A[b // a_div]) op(B[b // b_div]) + rb * E[b] on the tensor cores (3xTF32, csrc/gemm3x.cu), BLAS-style:
     A is stored (nb_a, M, K) -- (nb_a, K, M) with trans_a --, B is stored (nb_b, K, N) -- (nb_b, N, K) with trans_b;
     the last dimension of either may be a strided view (leading dimension = stride of dim -2).  row_alpha / row_beta are
-    (batch, M) per-row factors.  Returns None when the layout is not TMA-addressable (caller takes the CUDA-core
+    (batch, M) per-row factors.  ``store_transposed``: the result comes back as (batch, N, M) = D^T, E is given in that
+    layout too and the factors are (batch, N) -- choose the roles so that M is the memory-contiguous index of the
+    result (M = the tensor core's lane index: every store is then a full line).  Returns None when the layout is not TMA-addressable (caller takes the CUDA-core
     kernels); fp32 only."""
     require_cuda(A, B, row_alpha, E, row_beta)
     if A.dtype != torch.float32 or B.dtype != torch.float32:
@@ -140,22 +143,23 @@ def gemm3x(A: torch.Tensor, B: torch.Tensor, trans_a: bool = False, trans_b: boo
         if want_splits == 1:
             return None
         splits = 2
-    D = torch.empty(nb, M, N, dtype=out_dtype, device=A.device)
+    rows, cols = (N, M) if store_transposed else (M, N)  # stored shape of D and E
+    D = torch.empty(nb, rows, cols, dtype=out_dtype, device=A.device)
     ws_bytes = int(lib.lob_gemm3x_workspace_bytes(nb, M, N, K, int(splits)))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=A.device) if ws_bytes else None
-    ra = None if row_alpha is None else row_alpha.to(torch.float32).expand(nb, M).contiguous()
-    rb = None if row_beta is None else row_beta.to(torch.float32).expand(nb, M).contiguous()
+    ra = None if row_alpha is None else row_alpha.to(torch.float32).expand(nb, rows).contiguous()
+    rb = None if row_beta is None else row_beta.to(torch.float32).expand(nb, rows).contiguous()
     E3 = None
     if E is not None:
-        E3 = E.reshape(nb, M, N)
+        E3 = E.reshape(nb, rows, cols)
         if E3.stride(-1) != 1:
             E3 = E3.contiguous()
     status = lib.lob_gemm3x(
         nb, M, N, K, ptr(A3), 1 if trans_a else 0, A3.stride(1), A3.stride(0) if A3.shape[0] > 1 else 0, int(a_div),
         ptr(B3), 0 if trans_b else 1, B3.stride(1), B3.stride(0) if B3.shape[0] > 1 else 0, int(b_div),
-        ptr(D), _lib._DT[out_dtype], N, M * N, float(alpha), ptr(ra), M, ptr(E3),
-        0 if E3 is None else E3.stride(1), 0 if E3 is None else E3.stride(0), ptr(rb), M, int(splits), ptr(ws), ws_bytes,
-        stream(A))
+        ptr(D), _lib._DT[out_dtype], cols, M * N, float(alpha), ptr(ra), rows, ptr(E3),
+        0 if E3 is None else E3.stride(1), 0 if E3 is None else E3.stride(0), ptr(rb), rows,
+        1 if store_transposed else 0, int(splits), ptr(ws), ws_bytes, stream(A))
     if status == _lib.UNSUPPORTED:
         return None
     check(status, "lob_gemm3x")
@@ -571,13 +575,18 @@ def _kron_matmul_tc(factors, X, d):
             post = N // (pre * n)
             Ki = fl[i] if fl[i].shape[0] == 1 else fl[i][b0:b1]
             shared = Ki.shape[0] == 1
+            # operand roles are chosen so that the memory-contiguous index of the result is the GEMM's M (= lane) index:
+            # the kernel computes the transposed product and stores it transposed, every store a full line
             if i < len(sizes) - 1:
+                # Y (n x post) = K_i X  <=>  Y^T (post x n) = X^T K_i^T: A = X stored (K = n, M = post), B = K_i stored (N, K)
                 nbatch = nb * C * pre
-                out = gemm3x(Ki, cur.reshape(nbatch, n, post), a_div=(nbatch if shared else C * pre), batch=nbatch)
+                out = gemm3x(cur.reshape(nbatch, n, post), Ki, trans_a=True, trans_b=True,
+                             b_div=(nbatch if shared else C * pre), batch=nbatch, store_transposed=True)
             else:
+                # Y (pre x n) = X K_m^T  <=>  Y^T (n x pre) = K_m X^T: A = K_m (M = n, K), B = X stored (N = pre, K)
                 nbatch = nb * C
-                out = gemm3x(cur.reshape(nbatch, pre, n), Ki, trans_b=True, b_div=(nbatch if shared else C),
-                             batch=nbatch)
+                out = gemm3x(Ki, cur.reshape(nbatch, pre, n), trans_b=True, a_div=(nbatch if shared else C),
+                             batch=nbatch, store_transposed=True)
             if out is None:
                 raise _lib.LobError("Kronecker tensor-core chain: operand not TMA-addressable")
             cur = out

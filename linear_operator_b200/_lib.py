@@ -150,8 +150,8 @@ _SIGS = {
     "lob_gemm3x": (
         ctypes.c_int,
         [c_int64, c_int64, c_int64, c_int64, _P, c_int32, c_int64, c_int64, c_int64, _P, c_int32, c_int64, c_int64,
-         c_int64, _P, c_int32, c_int64, c_int64, c_double, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int32, _P,
-         c_size_t, _P],
+         c_int64, _P, c_int32, c_int64, c_int64, c_double, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int32,
+         c_int32, _P, c_size_t, _P],
     ),
     "lob_bilinear_dense": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int32, _P]),
     "lob_bilinear_diag": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P]),

@@ -8,7 +8,10 @@
 //
 // Operands are fp32 in global memory in either major-ness (UMMA "K-major": the contraction index is contiguous;
 // "MN-major": the row / column index is contiguous -- a row-major (K, N) matrix is an MN-major B operand), so no
-// caller ever transposes.  Each CTA computes one 128 x 128 tile of D over one K range:
+// caller ever transposes.  Persistent CTAs (one per SM) walk a static schedule of work items, each one 128 x 128 tile
+// of D for one batch element over one K range; the accumulators are double-buffered in TMEM (2 x (main + correction) =
+// 512 columns), so the epilogue of one work item overlaps the main loop of the next -- what makes short contractions
+// (Kronecker modes, K = 100; w U^T, K = 256) run at the same rate as long ones:
 //   warp 0       TMA producer: A and B tiles (128 x 32 fp32, SWIZZLE_128B) into a 3-stage ring
 //   warps 8-15   converters: lo = x - trunc_tf32(x) for both tiles, same offsets, smem -> smem (the tensor core reads the
 //                raw fp32 words as tf32, i.e. truncated: hi costs nothing)
@@ -44,11 +47,15 @@ struct G3Params {
   float alpha;
   float* partial;  // (batch, splits, M, N) raw partial sums when splits > 1
   int64_t M, N, K;
-  int tiles_n;
+  int tiles_m, tiles_n;
+  int64_t nbatch;
+  int64_t total;  // work items = batch * splits * tiles_m * tiles_n
   int splits;
   int64_t kps;           // K range per split (multiple of G3_BK)
   int64_t a_div, b_div;  // operand batch index = batch / div (shared / grouped operands)
   int a_mn, b_mn;
+  int d_trans;           // element (m, n) is stored at D[n * ldd + m] (E likewise; the row factors then index n):
+                         // lanes = m write consecutive addresses -- the layout to pick when m is the contiguous index
 };
 
 // MN-major operand tile: 4 regions of [32 k rows][32 floats = 128 B].  For 32-bit operands the tensor core accepts ONE
@@ -70,6 +77,27 @@ __device__ __forceinline__ uint64_t g3_desc(uint32_t tile_addr, int mn, int kste
   return ds::make_kmajor_desc<32>(tile_addr) + (uint64_t)((kstep * 32) >> 4);
 }
 
+// one unit of work: a 128 x 128 tile of D for one batch element over one K range
+struct G3Work {
+  int64_t batch, m0, n0, k_begin;
+  int split, nkb;
+};
+
+__device__ __forceinline__ G3Work g3_decode(const G3Params& p, int64_t w) {
+  G3Work o;
+  const int64_t ntile = (int64_t)p.tiles_m * p.tiles_n;
+  const int64_t tile = w % ntile, rest = w / ntile;
+  o.split = (int)(rest % p.splits);
+  o.batch = rest / p.splits;
+  const int64_t tn = tile / p.tiles_m, tm = tile - tn * p.tiles_m;  // consecutive work items share the B tile
+  o.m0 = tm * G3_BM;
+  o.n0 = tn * G3_BN;
+  o.k_begin = (int64_t)o.split * p.kps;
+  const int64_t k_end = min(p.K, o.k_begin + p.kps);
+  o.nkb = (int)((k_end - o.k_begin + G3_BK - 1) / G3_BK);
+  return o;
+}
+
 __global__ void __launch_bounds__(G3_THREADS, 1)
 k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, G3Params p) {
   using namespace ds;
@@ -79,18 +107,11 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   uint64_t* full = bars;                   // TMA -> converters, MMA
   uint64_t* empty = full + G3_STAGES;      // MMA (commit) -> TMA
   uint64_t* lo_full = empty + G3_STAGES;   // converters -> MMA
-  uint64_t* acc_full = lo_full + G3_STAGES;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = lo_full + G3_STAGES;  // [2] MMA (commit) -> epilogue
+  uint64_t* acc_empty = acc_full + 2;        // [2] epilogue -> MMA
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-  const int split = blockIdx.y;
-  const int64_t batch = blockIdx.z;
-  const int64_t m0 = (int64_t)tm * G3_BM, n0 = (int64_t)tn * G3_BN;
-  const int64_t k_begin = (int64_t)split * p.kps;
-  const int64_t k_end = min(p.K, k_begin + p.kps);
-  const int nkb = (int)((k_end - k_begin + G3_BK - 1) / G3_BK);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -100,11 +121,14 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       mbar_init(smem_u32(&empty[i]), 1);
       mbar_init(smem_u32(&lo_full[i]), G3_CONV_THREADS / 32);
     }
-    mbar_init(smem_u32(acc_full), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&acc_full[i]), 1);
+      mbar_init(smem_u32(&acc_empty[i]), 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_holder))
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_holder))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -118,29 +142,32 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     if (elect_one()) {
       uint64_t pol;
       asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-      const int ab = (int)(batch / p.a_div), bb = (int)(batch / p.b_div);
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(smem_u32(&empty[s]), ph ^ 1);
-        const uint32_t bar = smem_u32(&full[s]);
-        mbar_arrive_expect_tx(bar, 2 * G3_TILE_BYTES);
-        const uint32_t dst = smem_u32(smem + s * G3_STAGE_BYTES);
-        const int k0 = (int)(k_begin + (int64_t)kb * G3_BK);
-        if (!p.a_mn) {
-          tma_load_3d(dst, &tmA, bar, k0, (int)m0, ab, pol);
-        } else {
+      for (int64_t w = blockIdx.x; w < p.total; w += gridDim.x) {
+        const G3Work wk = g3_decode(p, w);
+        const int ab = (int)(wk.batch / p.a_div), bb = (int)(wk.batch / p.b_div);
+        for (int kb = 0; kb < wk.nkb; ++kb) {
+          mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+          const uint32_t bar = smem_u32(&full[s]);
+          mbar_arrive_expect_tx(bar, 2 * G3_TILE_BYTES);
+          const uint32_t dst = smem_u32(smem + s * G3_STAGE_BYTES);
+          const int k0 = (int)(wk.k_begin + (int64_t)kb * G3_BK);
+          if (!p.a_mn) {
+            tma_load_3d(dst, &tmA, bar, k0, (int)wk.m0, ab, pol);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * 4096, &tmA, bar, (int)m0 + 32 * j, k0, ab, pol);
-        }
-        if (!p.b_mn) {
-          tma_load_3d(dst + G3_TILE_BYTES, &tmB, bar, k0, (int)n0, bb, pol);
-        } else {
+            for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * 4096, &tmA, bar, (int)wk.m0 + 32 * j, k0, ab, pol);
+          }
+          if (!p.b_mn) {
+            tma_load_3d(dst + G3_TILE_BYTES, &tmB, bar, k0, (int)wk.n0, bb, pol);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            tma_load_3d(dst + G3_TILE_BYTES + j * 4096, &tmB, bar, (int)n0 + 32 * j, k0, bb, pol);
+            for (int j = 0; j < 4; ++j)
+              tma_load_3d(dst + G3_TILE_BYTES + j * 4096, &tmB, bar, (int)wk.n0 + 32 * j, k0, bb, pol);
+          }
+          if (++s == G3_STAGES) { s = 0; ph ^= 1; }
         }
-        if (++s == G3_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -148,91 +175,123 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const uint32_t idesc = make_idesc_tf32(G3_BM, G3_BN) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
                            ((uint32_t)(p.b_mn ? 1 : 0) << 16);
     int s = 0;
-    uint32_t ph = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      mbar_wait(smem_u32(&full[s]), ph);
-      mbar_wait(smem_u32(&lo_full[s]), ph);
+    uint32_t ph = 0, it = 0;
+    for (int64_t w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
+      const G3Work wk = g3_decode(p, w);
+      const uint32_t buf = it & 1;
+      mbar_wait(smem_u32(&acc_empty[buf]), ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator pair
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_addr = smem_u32(smem + s * G3_STAGE_BYTES);
-        const uint32_t b_addr = a_addr + G3_TILE_BYTES;
-        const uint32_t al_addr = a_addr + 2 * G3_TILE_BYTES, bl_addr = a_addr + 3 * G3_TILE_BYTES;
+      const uint32_t d_main = tmem_base + buf * (2 * G3_BN), d_corr = d_main + G3_BN;
+      for (int kb = 0; kb < wk.nkb; ++kb) {
+        mbar_wait(smem_u32(&full[s]), ph);
+        mbar_wait(smem_u32(&lo_full[s]), ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + s * G3_STAGE_BYTES);
+          const uint32_t b_addr = a_addr + G3_TILE_BYTES;
+          const uint32_t al_addr = a_addr + 2 * G3_TILE_BYTES, bl_addr = a_addr + 3 * G3_TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < G3_BK / 8; ++k) {
-          const uint64_t a_hi = g3_desc(a_addr, p.a_mn, k), b_hi = g3_desc(b_addr, p.b_mn, k);
-          const uint64_t a_lo = g3_desc(al_addr, p.a_mn, k), b_lo = g3_desc(bl_addr, p.b_mn, k);
-          // the small correction terms go to their own accumulator (columns 128..255): the main accumulator then takes
-          // one truncating fp32 add per k step instead of three, and the corrections are added once, in the epilogue
-          umma_tf32_ss(tmem_base, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
-          umma_tf32_ss(tmem_base + G3_BN, a_hi, b_lo, idesc, (kb | k) ? 1u : 0u);
-          umma_tf32_ss(tmem_base + G3_BN, a_lo, b_hi, idesc, 1u);
+          for (int k = 0; k < G3_BK / 8; ++k) {
+            const uint64_t a_hi = g3_desc(a_addr, p.a_mn, k), b_hi = g3_desc(b_addr, p.b_mn, k);
+            const uint64_t a_lo = g3_desc(al_addr, p.a_mn, k), b_lo = g3_desc(bl_addr, p.b_mn, k);
+            // the small correction terms go to their own accumulator: the main accumulator then takes one truncating
+            // fp32 add per k step instead of three, and the corrections are added once, in the epilogue
+            umma_tf32_ss(d_main, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
+            umma_tf32_ss(d_corr, a_hi, b_lo, idesc, (kb | k) ? 1u : 0u);
+            umma_tf32_ss(d_corr, a_lo, b_hi, idesc, 1u);
+          }
+          umma_commit(smem_u32(&empty[s]));
+          if (kb == wk.nkb - 1) umma_commit(smem_u32(&acc_full[buf]));
         }
-        umma_commit(smem_u32(&empty[s]));
-        if (kb == nkb - 1) umma_commit(smem_u32(acc_full));
+        __syncwarp();
+        if (++s == G3_STAGES) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++s == G3_STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ===================== epilogue: thread = output row =====================
+    // ===================== epilogue: thread = output row; overlaps the main loop of the next work item =============
     const int q = warp & 3;
-    const int64_t m = m0 + q * 32 + lane;
-    mbar_wait(smem_u32(acc_full), 0);
-    __syncwarp();
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool row_ok = m < p.M;
-    float* dst;
-    int64_t ld;
-    float ra = p.alpha, rb = 1.f;
-    const float* erow = nullptr;
-    if (p.splits > 1) {
-      dst = p.partial + ((batch * p.splits + split) * p.M + (row_ok ? m : 0)) * p.N;
-      ld = p.N;
-      ra = 1.f;
-    } else {
-      dst = p.D + batch * p.d_bs + (row_ok ? m : 0) * p.ldd;
-      ld = p.ldd;
-      if (row_ok) {
-        if (p.row_alpha) ra = p.row_alpha[batch * p.ra_bs + m];
-        if (p.E) {
-          erow = p.E + batch * p.e_bs + m * p.lde;
-          if (p.row_beta) rb = p.row_beta[batch * p.rb_bs + m];
+    uint32_t it = 0;
+    for (int64_t w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
+      const G3Work wk = g3_decode(p, w);
+      const uint32_t buf = it & 1;
+      const int64_t m = wk.m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      float* dst;
+      float ra = p.alpha, rb = 1.f;
+      const float* erow = nullptr;
+      if (p.splits > 1) {
+        dst = p.partial + ((wk.batch * p.splits + wk.split) * p.M + (row_ok ? m : 0)) * p.N;
+        ra = 1.f;
+      } else {
+        dst = p.D + wk.batch * p.d_bs + (row_ok ? m : 0) * p.ldd;
+        if (row_ok && !p.d_trans) {
+          if (p.row_alpha) ra = p.row_alpha[wk.batch * p.ra_bs + m];
+          if (p.E) {
+            erow = p.E + wk.batch * p.e_bs + m * p.lde;
+            if (p.row_beta) rb = p.row_beta[wk.batch * p.rb_bs + m];
+          }
         }
       }
-    }
-    (void)ld;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                        (erow == nullptr || (reinterpret_cast<uintptr_t>(erow) & 15) == 0);
+      const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                          (erow == nullptr || (reinterpret_cast<uintptr_t>(erow) & 15) == 0);
+      const bool trans = p.d_trans && p.splits == 1;
+      mbar_wait(smem_u32(&acc_full[buf]), (it >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (2 * G3_BN);
 #pragma unroll 1
-    for (int chunk = 0; chunk < G3_BN / 32; ++chunk) {
-      const int64_t nb = n0 + chunk * 32;
-      if (nb >= p.N) break;  // warp-uniform
-      uint32_t r[32], rc[32];
-      DS_LD32(taddr + chunk * 32, r);
-      DS_LD32(taddr + G3_BN + chunk * 32, rc);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (!row_ok) continue;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(rc[i]));
-      if (vec_ok && nb + 32 <= p.N) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float4 v = make_float4(__uint_as_float(r[i]) * ra, __uint_as_float(r[i + 1]) * ra,
-                                 __uint_as_float(r[i + 2]) * ra, __uint_as_float(r[i + 3]) * ra);
-          if (erow) {
-            const float4 e = *reinterpret_cast<const float4*>(erow + nb + i);
-            v.x = fmaf(rb, e.x, v.x); v.y = fmaf(rb, e.y, v.y); v.z = fmaf(rb, e.z, v.z); v.w = fmaf(rb, e.w, v.w);
-          }
-          *reinterpret_cast<float4*>(dst + nb + i) = v;
+      for (int chunk = 0; chunk < G3_BN / 32; ++chunk) {
+        const int64_t nb = wk.n0 + chunk * 32;
+        if (nb >= p.N) break;  // warp-uniform
+        uint32_t r[32], rc[32];
+        DS_LD32(taddr + chunk * 32, r);
+        DS_LD32(taddr + G3_BN + chunk * 32, rc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (chunk == G3_BN / 32 - 1 || nb + 32 >= p.N) {
+          // last TMEM read of this work item: hand the accumulator pair back before the global stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
         }
-      } else {
+        if (!row_ok) continue;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (nb + i < p.N) {
-            float v = __uint_as_float(r[i]) * ra;
-            if (erow) v = fmaf(rb, erow[nb + i], v);
-            dst[nb + i] = v;
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(rc[i]));
+        if (trans) {
+          // element (m, n) -> D[n * ldd + m]: for every n the 32 lanes (consecutive m) write one 128-byte line
+          float* Db = p.D + wk.batch * p.d_bs + m;
+          const float* Eb = p.E ? p.E + wk.batch * p.e_bs + m : nullptr;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int64_t n = nb + i;
+            if (n < p.N) {
+              const float fa = p.row_alpha ? __ldg(p.row_alpha + wk.batch * p.ra_bs + n) : p.alpha;
+              float v = __uint_as_float(r[i]) * fa;
+              if (Eb) {
+                const float fb = p.row_beta ? __ldg(p.row_beta + wk.batch * p.rb_bs + n) : 1.f;
+                v = fmaf(fb, Eb[n * p.lde], v);
+              }
+              Db[n * p.ldd] = v;
+            }
+          }
+        } else if (vec_ok && nb + 32 <= p.N) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 v = make_float4(__uint_as_float(r[i]) * ra, __uint_as_float(r[i + 1]) * ra,
+                                   __uint_as_float(r[i + 2]) * ra, __uint_as_float(r[i + 3]) * ra);
+            if (erow) {
+              const float4 e = *reinterpret_cast<const float4*>(erow + nb + i);
+              v.x = fmaf(rb, e.x, v.x); v.y = fmaf(rb, e.y, v.y); v.z = fmaf(rb, e.z, v.z); v.w = fmaf(rb, e.w, v.w);
+            }
+            *reinterpret_cast<float4*>(dst + nb + i) = v;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (nb + i < p.N) {
+              float v = __uint_as_float(r[i]) * ra;
+              if (erow) v = fmaf(rb, erow[nb + i], v);
+              dst[nb + i] = v;
+            }
           }
         }
       }
@@ -243,26 +302,29 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     constexpr int NV = 2 * G3_TILE_BYTES / 16 / G3_CONV_THREADS;  // 8 x 16 bytes per thread per k block
     int s = 0;
     uint32_t ph = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      mbar_wait(smem_u32(&full[s]), ph);
-      const uint4* src = reinterpret_cast<const uint4*>(smem + s * G3_STAGE_BYTES) + ct;
-      uint4* dstv = reinterpret_cast<uint4*>(smem + s * G3_STAGE_BYTES + 2 * G3_TILE_BYTES) + ct;
-      uint4 v[NV];
+    for (int64_t w = blockIdx.x; w < p.total; w += gridDim.x) {
+      const int nkb = g3_decode(p, w).nkb;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(smem_u32(&full[s]), ph);
+        const uint4* src = reinterpret_cast<const uint4*>(smem + s * G3_STAGE_BYTES) + ct;
+        uint4* dstv = reinterpret_cast<uint4*>(smem + s * G3_STAGE_BYTES + 2 * G3_TILE_BYTES) + ct;
+        uint4 v[NV];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] = src[i * G3_CONV_THREADS];
+        for (int i = 0; i < NV; ++i) v[i] = src[i * G3_CONV_THREADS];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        uint4 o;
-        o.x = __float_as_uint(__uint_as_float(v[i].x) - __uint_as_float(v[i].x & 0xFFFFE000u));
-        o.y = __float_as_uint(__uint_as_float(v[i].y) - __uint_as_float(v[i].y & 0xFFFFE000u));
-        o.z = __float_as_uint(__uint_as_float(v[i].z) - __uint_as_float(v[i].z & 0xFFFFE000u));
-        o.w = __float_as_uint(__uint_as_float(v[i].w) - __uint_as_float(v[i].w & 0xFFFFE000u));
-        dstv[i * G3_CONV_THREADS] = o;
+        for (int i = 0; i < NV; ++i) {
+          uint4 o;
+          o.x = __float_as_uint(__uint_as_float(v[i].x) - __uint_as_float(v[i].x & 0xFFFFE000u));
+          o.y = __float_as_uint(__uint_as_float(v[i].y) - __uint_as_float(v[i].y & 0xFFFFE000u));
+          o.z = __float_as_uint(__uint_as_float(v[i].z) - __uint_as_float(v[i].z & 0xFFFFE000u));
+          o.w = __float_as_uint(__uint_as_float(v[i].w) - __uint_as_float(v[i].w & 0xFFFFE000u));
+          dstv[i * G3_CONV_THREADS] = o;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&lo_full[s]));
+        if (++s == G3_STAGES) { s = 0; ph ^= 1; }
       }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&lo_full[s]));
-      if (++s == G3_STAGES) { s = 0; ph ^= 1; }
     }
   }
 
@@ -271,7 +333,7 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -280,17 +342,19 @@ template <typename TO>
 __global__ void __launch_bounds__(256)
 k_g3_reduce(G3Params p, TO* __restrict__ out) {
   const int64_t total = p.M * p.N;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t batch = blockIdx.y;
-  if (idx >= total) return;
+  const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= total * p.nbatch) return;
+  const int64_t batch = gidx / total, idx = gidx - batch * total;
   const int64_t m = idx / p.N, n = idx - m * p.N;
   const float* src = p.partial + batch * p.splits * total + idx;
   double s = 0.0;
   for (int i = 0; i < p.splits; ++i) s += (double)src[(int64_t)i * total];
-  double ra = p.row_alpha ? (double)p.row_alpha[batch * p.ra_bs + m] : (double)p.alpha;
+  const int64_t f = p.d_trans ? n : m;  // index of the row factors
+  const int64_t o_r = p.d_trans ? n : m, o_c = p.d_trans ? m : n;
+  double ra = p.row_alpha ? (double)p.row_alpha[batch * p.ra_bs + f] : (double)p.alpha;
   double v = s * ra;
-  if (p.E) v += (p.row_beta ? (double)p.row_beta[batch * p.rb_bs + m] : 1.0) * (double)p.E[batch * p.e_bs + m * p.lde + n];
-  out[batch * p.d_bs + m * p.ldd + n] = (TO)v;
+  if (p.E) v += (p.row_beta ? (double)p.row_beta[batch * p.rb_bs + f] : 1.0) * (double)p.E[batch * p.e_bs + o_r * p.lde + o_c];
+  out[batch * p.d_bs + o_r * p.ldd + o_c] = (TO)v;
 }
 
 typedef CUresult (*PFN_encodeTiled_g3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -333,6 +397,13 @@ static bool g3_make_map(CUtensorMap* tm, const float* ptr, int mn, int64_t rows,
   return r == CUDA_SUCCESS;
 }
 
+// Split-K policy.  Two reasons to split: (1) parallelism when there are fewer tiles than SMs; (2) accuracy -- the
+// tensor core adds into its fp32 accumulator with truncation, an error that grows linearly with the number of k steps
+// accumulated in TMEM (measured at K = 10^7: 6e-4 relative with 37 splits, 2e-5 with 1024), so one split never
+// accumulates more than G3_MAX_K_PER_SPLIT contraction indices; the partial sums are added in double.
+constexpr int64_t G3_MAX_K_PER_SPLIT = 4096;
+constexpr int64_t G3_MAX_PARTIAL_BYTES = 4LL << 30;
+
 static int g3_pick_splits(int64_t batch, int64_t M, int64_t N, int64_t K, int requested) {
   const int64_t tiles = batch * cdiv(M, G3_BM) * cdiv(N, G3_BN);
   const int64_t max_splits = std::max<int64_t>(1, cdiv(K, 8 * G3_BK));  // at least 8 k blocks per split
@@ -340,9 +411,12 @@ static int g3_pick_splits(int64_t batch, int64_t M, int64_t N, int64_t K, int re
   if (s <= 0) {
     s = 1;
     if (tiles < kNumSMs) s = cdiv(2 * kNumSMs, tiles);
+    s = std::max<int64_t>(s, cdiv(K, G3_MAX_K_PER_SPLIT));
+    const int64_t cap = std::max<int64_t>(1, G3_MAX_PARTIAL_BYTES / (batch * M * N * (int64_t)sizeof(float)));
+    if (s > cap) s = cap;
   }
   if (s > max_splits) s = max_splits;
-  if (s > 1024) s = 1024;
+  if (s > 65535) s = 65535;
   if (s < 1) s = 1;
   // every split must own at least one k block
   int64_t kps = cdiv(cdiv(K, s), G3_BK) * G3_BK;
@@ -370,18 +444,17 @@ extern "C" int lob_gemm3x(int64_t batch, int64_t M, int64_t N, int64_t K, const 
                           int64_t b_batch_stride, int64_t b_batch_div, void* D, int32_t d_dtype, int64_t ldd,
                           int64_t d_batch_stride, double alpha, const void* row_alpha, int64_t row_alpha_batch_stride,
                           const void* E, int64_t lde, int64_t e_batch_stride, const void* row_beta,
-                          int64_t row_beta_batch_stride, int32_t requested_splits, void* ws, size_t ws_bytes,
-                          void* stream) {
+                          int64_t row_beta_batch_stride, int32_t d_trans, int32_t requested_splits, void* ws,
+                          size_t ws_bytes, void* stream) {
   LOB_REQUIRE(batch > 0 && M > 0 && N > 0 && K > 0, "lob_gemm3x: sizes must be positive");
   LOB_REQUIRE(A && B && D, "lob_gemm3x: NULL pointer");
   LOB_REQUIRE(a_batch_div >= 1 && b_batch_div >= 1, "lob_gemm3x: batch divisors must be >= 1");
-  LOB_REQUIRE(batch <= 65535, "lob_gemm3x: batch > 65535 not supported");
   LOB_REQUIRE(d_dtype == LOB_F32 || d_dtype == LOB_F64, "lob_gemm3x: output dtype must be LOB_F32 or LOB_F64");
   cudaStream_t st = (cudaStream_t)stream;
   const int splits = g3_pick_splits(batch, M, N, K, requested_splits);
   if (d_dtype == LOB_F64 && splits == 1) return fail(LOB_ERR_UNSUPPORTED, "lob_gemm3x: fp64 output needs the split-K path");
   const int64_t tiles_m = cdiv(M, G3_BM), tiles_n = cdiv(N, G3_BN);
-  if (tiles_m * tiles_n >= (1LL << 31) || splits > 65535) return fail(LOB_ERR_UNSUPPORTED, "lob_gemm3x: grid too large");
+  if (tiles_m >= (1LL << 31) || tiles_n >= (1LL << 31)) return fail(LOB_ERR_UNSUPPORTED, "lob_gemm3x: too many tiles");
   CUtensorMap tmA, tmB;
   if (!g3_make_map(&tmA, (const float*)A, a_mn, M, K, lda, a_batch_stride, cdiv(batch, a_batch_div)) ||
       !g3_make_map(&tmB, (const float*)B, b_mn, N, K, ldb, b_batch_stride, cdiv(batch, b_batch_div)))
@@ -402,24 +475,28 @@ extern "C" int lob_gemm3x(int64_t batch, int64_t M, int64_t N, int64_t K, const 
   p.M = M;
   p.N = N;
   p.K = K;
+  p.tiles_m = (int)tiles_m;
   p.tiles_n = (int)tiles_n;
+  p.nbatch = batch;
+  p.total = batch * splits * tiles_m * tiles_n;
   p.splits = splits;
   p.kps = cdiv(cdiv(K, splits), G3_BK) * G3_BK;
   p.a_div = a_batch_div;
   p.b_div = b_batch_div;
   p.a_mn = a_mn ? 1 : 0;
   p.b_mn = b_mn ? 1 : 0;
+  p.d_trans = d_trans ? 1 : 0;
   if (splits > 1) {
     const size_t need = (size_t)batch * splits * M * N * sizeof(float);
     LOB_REQUIRE(ws && ws_bytes >= need, "lob_gemm3x: workspace too small for the split-K partial sums");
     p.partial = (float*)ws;
   }
   LOB_CUDA(cudaFuncSetAttribute(k_gemm3x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G3_SMEM));
-  dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)splits, (unsigned)batch);
+  const unsigned grid = (unsigned)std::min<int64_t>(p.total, kNumSMs);
   k_gemm3x<<<grid, G3_THREADS, G3_SMEM, st>>>(tmA, tmB, p);
   LOB_TRY(check_launch("k_gemm3x"));
   if (splits > 1) {
-    dim3 rgrid((unsigned)cdiv(M * N, 256), (unsigned)batch);
+    const unsigned rgrid = (unsigned)cdiv(batch * M * N, 256);
     if (d_dtype == LOB_F64)
       k_g3_reduce<double><<<rgrid, 256, 0, st>>>(p, (double*)D);
     else

@@ -96,6 +96,7 @@ class AddedDiagLinearOperator(SumLinearOperator):
                 return _kernels.dense_matmul(tsr, v, d=d)
 
             closure.fused = lambda v: _kernels.dense_matmul(tsr, v, d=d, want_dots=True)
+            closure.graph_spec = (tsr, d)  # small solves replay as one CUDA graph (settings.cuda_graphs)
             return closure
         return self._matmul
 

@@ -33,6 +33,7 @@ class DenseLinearOperator(LinearOperator):
             return _kernels.dense_matmul(tsr, v)
 
         closure.fused = lambda v: _kernels.dense_matmul(tsr, v, want_dots=True)
+        closure.graph_spec = (tsr, None)  # lets linear_cg replay small solves as one CUDA graph (settings.cuda_graphs)
         return closure
 
     def _bilinear_derivative(self, left_vecs, right_vecs):  # :69-71: left right^T, one rank-C outer-product kernel

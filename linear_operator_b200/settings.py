@@ -200,6 +200,17 @@ class deterministic_probes(_Flag):
     probe_vectors = None
 
 
+class cuda_graphs(_Flag):
+    """Not in the reference.  Small dense problems (the operator at most ``cuda_graphs.max_operator_bytes``) are
+    launch-bound: ~90 kernel launches for a 21-iteration solve of N = 512.  With this flag on (default) linear_cg
+    replays the whole fixed-length part of the solve as ONE CUDA graph on solver-owned static buffers (inputs are copied
+    in, a few MB) and reads the control words once at the end; results are bit-identical to the eager launches."""
+
+    _default = True
+    max_operator_bytes = 32 << 20
+    max_rhs_bytes = 8 << 20
+
+
 class debug(_Flag):
     """Argument checking; default on (:265-275)."""
 

@@ -21,6 +21,147 @@ def _default_preconditioner(x):
     return x.clone()
 
 
+# ------------------------------------------------------------------------------------------------------------
+# CUDA-graph replay of small dense solves (settings.cuda_graphs)
+# ------------------------------------------------------------------------------------------------------------
+_GRAPHS = {}
+
+
+class _GraphedDenseCg:
+    """The launches of one un-preconditioned mBCG solve on a dense (+ diagonal) operator -- setup, initial residual and
+    direction, and the first ``n_graph`` iterations (every iteration before the reference's stop rule can fire) --
+    captured once into a CUDA graph over static buffers.  The kernels are the eager path's, in the same order, so the
+    numbers are bit-identical; what disappears is ~4 host launches per iteration."""
+
+    def __init__(self, A, d, rhs_c, p, n_graph, n_tridiag):
+        from .. import _kernels
+
+        lib = _lib.load()
+        dev = rhs_c.device
+        self.p, self.n_graph = p, n_graph
+        self.A = torch.empty(A.shape, dtype=A.dtype, device=dev)
+        self.d = None
+        self.d_const = False
+        if d is not None:
+            self.d_const = d.shape[-1] == 1 or d.stride(-1) == 0
+            self.d = torch.empty(*d.shape[:-1], 1 if self.d_const else d.shape[-1], dtype=d.dtype, device=dev)
+        self.rhs = torch.empty_like(rhs_c)
+        self.ws = workspace(lib.lob_cg_workspace_bytes(ctypes_byref(p)), dev)
+        self.rhs_n = torch.empty_like(rhs_c)
+        self.x = torch.empty_like(rhs_c)
+        self.r = torch.empty_like(rhs_c)
+        self.pvec = torch.empty_like(rhs_c)
+        self.t_mat = None
+        if n_tridiag:
+            self.t_mat = torch.empty(n_tridiag, *rhs_c.shape[:-2], p.n_tridiag_iter, p.n_tridiag_iter, dtype=rhs_c.dtype,
+                                     device=dev)
+        self._kernels = _kernels
+        self.load(A, d, rhs_c)
+        # warm-up on a side stream (lazy module / attribute initialisation must not happen inside the capture)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.body()
+
+    def load(self, A, d, rhs_c):
+        self.A.copy_(A)
+        if self.d is not None:
+            self.d.copy_(d[..., :1] if self.d_const else d)
+        self.rhs.copy_(rhs_c)
+
+    def iterate(self, k):
+        lib, p, st = _lib.load(), self.p, stream(self.rhs)
+        ap, dots, n_parts = self._kernels.dense_matmul(self.A, self.pvec, d=self.d, want_dots=True)
+        check(lib.lob_cg_step_xr(ctypes_byref(p), ptr(self.ws), k, ptr(ap), ptr(self.pvec), ptr(self.x), ptr(self.r),
+                                 ptr(dots), n_parts, st), "lob_cg_step_xr")
+        check(lib.lob_cg_step_p(ctypes_byref(p), ptr(self.ws), k, None, ptr(self.r), ptr(self.pvec), ptr(self.t_mat),
+                                None, 0, st), "lob_cg_step_p")
+
+    def body(self):
+        lib, p, st = _lib.load(), self.p, stream(self.rhs)
+        check(lib.lob_cg_setup(ctypes_byref(p), ptr(self.ws), ptr(self.rhs), None, ptr(self.rhs_n), ptr(self.x),
+                               ptr(self.t_mat), st), "lob_cg_setup")
+        check(lib.lob_cg_residual_init(ctypes_byref(p), ptr(self.ws), ptr(self.rhs_n), None, ptr(self.r), st),
+              "lob_cg_residual_init")
+        check(lib.lob_cg_direction_init(ctypes_byref(p), ptr(self.ws), ptr(self.r), ptr(self.r), ptr(self.pvec), None, 0,
+                                        st), "lob_cg_direction_init")
+        for k in range(self.n_graph):
+            self.iterate(k)
+
+
+def _graph_eligible(spec, rhs, precond, have_guess, skip_initial):
+    if spec is None or precond or have_guess or not skip_initial or settings.cuda_graphs.off():
+        return False
+    A, d = spec
+    if not (torch.is_tensor(A) and A.is_cuda and rhs.is_cuda) or A.dtype != rhs.dtype:
+        return False
+    if A.shape[-1] != A.shape[-2] or A.shape[:-2] != rhs.shape[:-2]:
+        return False
+    if A.numel() * A.element_size() > settings.cuda_graphs.max_operator_bytes:
+        return False
+    if rhs.numel() * rhs.element_size() > settings.cuda_graphs.max_rhs_bytes:
+        return False
+    return not torch.cuda.is_current_stream_capturing()
+
+
+def _warn_not_converged(status, n_iter, tolerance):
+    if not status.tolerance_reached and n_iter > 0 and status.iterations > 0:  # :337-347
+        warnings.warn(
+            "CG terminated in {} iterations with average residual norm {}"
+            " which is larger than the tolerance of {} specified by"
+            " linear_operator.settings.cg_tolerance."
+            " If performance is affected, consider raising the maximum number of CG iterations by running code in"
+            " a linear_operator.settings.max_cg_iterations(value) context.".format(
+                status.iterations, status.residual_norm_mean, tolerance
+            ),
+            NumericalWarning,
+        )
+
+
+def _graphed_dense_solve(spec, rhs_c, p, n_iter, n_tridiag, first_stop, tolerance):
+    A, d = spec
+    lib = _lib.load()
+    n_graph = min(n_iter, first_stop + 1)
+    key = (rhs_c.device.index, rhs_c.dtype, tuple(A.shape), None if d is None else (tuple(d.shape), d.stride(-1) == 0),
+           tuple(rhs_c.shape), n_graph, p.n_tridiag, p.n_tridiag_iter, p.max_iter, p.n_iter, p.tolerance, p.eps,
+           p.stop_updating_after)
+    g = _GRAPHS.get(key)
+    if g is None:
+        if len(_GRAPHS) >= 16:  # bounded cache of static buffers
+            _GRAPHS.pop(next(iter(_GRAPHS)))
+        g = _GRAPHS[key] = _GraphedDenseCg(A, d, rhs_c, p, n_graph, n_tridiag)
+    else:
+        g.load(A, d, rhs_c)
+    g.graph.replay()
+    status = CgStatus()
+    st = stream(rhs_c)
+
+    def poll():
+        check(lib.lob_cg_poll_sync(ctypes_byref(g.p), ptr(g.ws), ctypes_byref(status), st), "lob_cg_poll_sync")
+        if status.nan_detected:
+            raise RuntimeError("NaNs encountered when trying to perform matrix-vector multiplication")
+        return status.stop
+
+    stopped = poll()
+    k = n_graph
+    while not stopped and k < n_iter:  # the stop rule did not fire inside the captured part: continue launch by launch
+        g.iterate(k)
+        stopped = poll()
+        k += 1
+    check(lib.lob_cg_finish(ctypes_byref(g.p), ptr(g.ws), ptr(g.x), st), "lob_cg_finish")
+    _warn_not_converged(status, n_iter, tolerance)
+    x = g.x.clone()
+    if n_tridiag:
+        last = status.last_tridiag_iter + 1
+        return x, g.t_mat[..., :last, :last].contiguous()
+    return x, None
+
+
 @_lib.device_guard
 def linear_cg(
     matmul_closure,
@@ -118,6 +259,18 @@ def linear_cg(
     p = make_params(B)
     dev = rhs_c.device
     st = stream(rhs_c)
+
+    # first iteration index at which the reference's stop rule (:302-306) can fire
+    first_stop = min(10, max_iter - 1)
+    if n_tridiag:
+        first_stop = max(first_stop, min(n_tridiag_iter, max_iter - 1))
+
+    graph_spec = getattr(matmul_closure, "graph_spec", None)
+    if n_iter > 0 and _graph_eligible(graph_spec, rhs_c, precond, have_guess, _skip_initial_matmul):
+        result, t_mat = _graphed_dense_solve(graph_spec, rhs_c, p, n_iter, n_tridiag, first_stop, tolerance)
+        if is_vector:
+            result = result.squeeze(-1)
+        return (result, t_mat) if n_tridiag else result
     ws = workspace(lib.lob_cg_workspace_bytes(ctypes_byref(p)), dev)
     rhs_n = torch.empty_like(rhs_c)
     x = torch.empty_like(rhs_c)
@@ -176,11 +329,6 @@ def linear_cg(
     check(lib.lob_cg_direction_init(ctypes_byref(p), ptr(ws), ptr(r), ptr(z), ptr(pvec), ptr(rz_parts), n_rz, st),
           "lob_cg_direction_init")
 
-    # first iteration index at which the reference's stop rule (:302-306) can fire
-    first_stop = min(10, max_iter - 1)
-    if n_tridiag:
-        first_stop = max(first_stop, min(n_tridiag_iter, max_iter - 1))
-
     polled = False
     for k in range(n_iter):
         if fused is not None:
@@ -211,17 +359,7 @@ def linear_cg(
 
     check(lib.lob_cg_finish(ctypes_byref(p), ptr(ws), ptr(x), st), "lob_cg_finish")  # :335
 
-    if not status.tolerance_reached and n_iter > 0 and status.iterations > 0:  # :337-347
-        warnings.warn(
-            "CG terminated in {} iterations with average residual norm {}"
-            " which is larger than the tolerance of {} specified by"
-            " linear_operator.settings.cg_tolerance."
-            " If performance is affected, consider raising the maximum number of CG iterations by running code in"
-            " a linear_operator.settings.max_cg_iterations(value) context.".format(
-                status.iterations, status.residual_norm_mean, tolerance
-            ),
-            NumericalWarning,
-        )
+    _warn_not_converged(status, n_iter, tolerance)
 
     result = x
     if is_vector:

@@ -55,6 +55,13 @@ def test_gemm3x_epilogue_and_grouped_batches():
                           E=R.unsqueeze(0), row_beta=(1.0 / sig).unsqueeze(0))
     want = (R.double() - w.double() @ U.double().mT) / sig.double().unsqueeze(-1)
     check(npy(out[0]), npy(want), TOL)
+    # the same product with swapped roles and a transposed store: x^T = U w^T, written as (B, N)
+    out_t = _kernels.gemm3x(U.unsqueeze(0), w.unsqueeze(0), trans_b=True, row_alpha=(-1.0 / sig).unsqueeze(0),
+                            E=R.unsqueeze(0), row_beta=(1.0 / sig).unsqueeze(0), store_transposed=True)
+    assert out_t.shape == (1, Bsz, Nl)
+    check(npy(out_t[0]), npy(want), TOL)
+    Dt = _kernels.gemm3x(R.unsqueeze(0), U.unsqueeze(0), splits=4, store_transposed=True)  # split-K + transposed store
+    check(npy(Dt[0]), npy((R.double() @ U.double()).mT), TOL)
     # grouped operand batches: A[b // 3] B[b]
     A = rnd(2, 96, 40, gen=gen)
     Bm = rnd(6, 40, 72, gen=gen)

@@ -270,3 +270,42 @@ def test_cfg5_lowrank_shared_root_n1e6_vs_oracle(dtype, rtol):
     check(npy(x), xo, rtol)
     check(npy(iq), (rn * xo).sum((-2, -1)), rtol)
     check(npy(ld), ldo, rtol)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CUDA-graph replay of small dense solves (settings.cuda_graphs)
+# ------------------------------------------------------------------------------------------------------------
+def test_cuda_graph_replay_is_bit_identical_to_eager_launches():
+    """BASELINE configs[0]-sized problems are launch-bound; linear_cg replays the fixed-length part of the solve as one
+    CUDA graph on static buffers.  Same kernels, same order: the results must not differ by a bit, also when the graph
+    is replayed on new data and when the stop rule only fires after the captured part."""
+    from linear_operator_b200.utils import linear_cg as cg_module  # noqa: F401
+    import linear_operator_b200.utils.linear_cg as cgm
+
+    gen = torch.Generator(device=DEV).manual_seed(17)
+    n, s = 512, 16
+    outs = {}
+    for flag in (False, True, True):  # eager, capture + replay, replay on new inputs below
+        res = []
+        for trial in range(2):
+            g2 = torch.Generator(device=DEV).manual_seed(100 + trial)
+            W = torch.randn(n, 64, device=DEV, dtype=torch.float64, generator=g2) / 8
+            K = W @ W.mT
+            d = torch.full((n,), 0.5 + 0.1 * trial, device=DEV, dtype=torch.float64)
+            rhs = torch.randn(n, 1, device=DEV, dtype=torch.float64, generator=g2)
+            probes = torch.randn(n, s, device=DEV, dtype=torch.float64, generator=g2)
+            probes = probes / probes.norm(dim=-2, keepdim=True)
+            op = Injected(DenseLinearOperator(K), DiagLinearOperator(d))
+            op.probes = probes
+            with settings.cuda_graphs(flag), settings.max_cholesky_size(0), settings.num_trace_samples(s):
+                iq, ld = op.inv_quad_logdet(rhs, logdet=True)
+                with settings.cg_tolerance(1e-9), settings.max_cg_iterations(300):
+                    sol = op.solve(rhs)  # the stop rule fires long after the captured iterations
+            res.append((iq.clone(), ld.clone(), sol.clone()))
+        outs.setdefault(flag, []).append(res)
+    assert len(cgm._GRAPHS) >= 1  # the graph path really ran
+    eager = outs[False][0]
+    for replayed in outs[True]:
+        for (a, b, c), (a2, b2, c2) in zip(eager, replayed):
+            assert torch.equal(a, a2) and torch.equal(b, b2) and torch.equal(c, c2)
+    del gen
