@@ -575,18 +575,13 @@ def _kron_matmul_tc(factors, X, d):
             post = N // (pre * n)
             Ki = fl[i] if fl[i].shape[0] == 1 else fl[i][b0:b1]
             shared = Ki.shape[0] == 1
-            # operand roles are chosen so that the memory-contiguous index of the result is the GEMM's M (= lane) index:
-            # the kernel computes the transposed product and stores it transposed, every store a full line
             if i < len(sizes) - 1:
-                # Y (n x post) = K_i X  <=>  Y^T (post x n) = X^T K_i^T: A = X stored (K = n, M = post), B = K_i stored (N, K)
                 nbatch = nb * C * pre
-                out = gemm3x(cur.reshape(nbatch, n, post), Ki, trans_a=True, trans_b=True,
-                             b_div=(nbatch if shared else C * pre), batch=nbatch, store_transposed=True)
+                out = gemm3x(Ki, cur.reshape(nbatch, n, post), a_div=(nbatch if shared else C * pre), batch=nbatch)
             else:
-                # Y (pre x n) = X K_m^T  <=>  Y^T (n x pre) = K_m X^T: A = K_m (M = n, K), B = X stored (N = pre, K)
                 nbatch = nb * C
-                out = gemm3x(Ki, cur.reshape(nbatch, pre, n), trans_b=True, a_div=(nbatch if shared else C),
-                             batch=nbatch, store_transposed=True)
+                out = gemm3x(cur.reshape(nbatch, pre, n), Ki, trans_b=True, b_div=(nbatch if shared else C),
+                             batch=nbatch)
             if out is None:
                 raise _lib.LobError("Kronecker tensor-core chain: operand not TMA-addressable")
             cur = out

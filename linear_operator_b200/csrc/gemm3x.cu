@@ -50,6 +50,8 @@ struct G3Params {
   int tiles_m, tiles_n;
   int64_t nbatch;
   int64_t total;  // work items = batch * splits * tiles_m * tiles_n
+  int64_t jobs;   // column jobs = batch * splits * tiles_n
+  int sched_flat;
   int splits;
   int64_t kps;           // K range per split (multiple of G3_BK)
   int64_t a_div, b_div;  // operand batch index = batch / div (shared / grouped operands)
@@ -83,19 +85,33 @@ struct G3Work {
   int split, nkb;
 };
 
-__device__ __forceinline__ G3Work g3_decode(const G3Params& p, int64_t w) {
-  G3Work o;
-  const int64_t ntile = (int64_t)p.tiles_m * p.tiles_n;
-  const int64_t tile = w % ntile, rest = w / ntile;
+// Static schedule.  A "column job" J is one (batch element, K range, 128-column block) of D; CTA c owns the jobs
+// J = c, c + G, c + 2G, ... and walks the row blocks of each job in order.  Consecutive work items of a CTA therefore
+// share their B tile (L2 hit), and the CTAs running side by side write neighbouring column blocks of the SAME rows --
+// with row strides of tens of MB (x = (R - w U^T)/sigma is 512 x 10^7) that locality is worth 30 % (measured: 68 vs
+// 95 ms for the opposite order).  With many row blocks per job (sched_flat) the items are dealt out one by one instead,
+// which balances better.
+__device__ __forceinline__ bool g3_decode(const G3Params& p, int64_t it, G3Work& o) {
+  int64_t J, tm;
+  if (p.sched_flat) {
+    const int64_t w = blockIdx.x + it * (int64_t)gridDim.x;
+    if (w >= p.total) return false;
+    tm = w % p.tiles_m;
+    J = w / p.tiles_m;
+  } else {
+    J = blockIdx.x + (it / p.tiles_m) * (int64_t)gridDim.x;
+    if (J >= p.jobs) return false;
+    tm = it % p.tiles_m;
+  }
+  const int64_t tn = J % p.tiles_n, rest = J / p.tiles_n;
   o.split = (int)(rest % p.splits);
   o.batch = rest / p.splits;
-  const int64_t tn = tile / p.tiles_m, tm = tile - tn * p.tiles_m;  // consecutive work items share the B tile
   o.m0 = tm * G3_BM;
   o.n0 = tn * G3_BN;
   o.k_begin = (int64_t)o.split * p.kps;
   const int64_t k_end = min(p.K, o.k_begin + p.kps);
   o.nkb = (int)((k_end - o.k_begin + G3_BK - 1) / G3_BK);
-  return o;
+  return true;
 }
 
 __global__ void __launch_bounds__(G3_THREADS, 1)
@@ -144,8 +160,8 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
       int s = 0;
       uint32_t ph = 0;
-      for (int64_t w = blockIdx.x; w < p.total; w += gridDim.x) {
-        const G3Work wk = g3_decode(p, w);
+      G3Work wk;
+      for (int64_t wi = 0; g3_decode(p, wi, wk); ++wi) {
         const int ab = (int)(wk.batch / p.a_div), bb = (int)(wk.batch / p.b_div);
         for (int kb = 0; kb < wk.nkb; ++kb) {
           mbar_wait(smem_u32(&empty[s]), ph ^ 1);
@@ -176,8 +192,8 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                            ((uint32_t)(p.b_mn ? 1 : 0) << 16);
     int s = 0;
     uint32_t ph = 0, it = 0;
-    for (int64_t w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
-      const G3Work wk = g3_decode(p, w);
+    G3Work wk;
+    for (; g3_decode(p, it, wk); ++it) {
       const uint32_t buf = it & 1;
       mbar_wait(smem_u32(&acc_empty[buf]), ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator pair
       tc_fence_after();
@@ -211,8 +227,8 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     // ===================== epilogue: thread = output row; overlaps the main loop of the next work item =============
     const int q = warp & 3;
     uint32_t it = 0;
-    for (int64_t w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
-      const G3Work wk = g3_decode(p, w);
+    G3Work wk;
+    for (; g3_decode(p, it, wk); ++it) {
       const uint32_t buf = it & 1;
       const int64_t m = wk.m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
@@ -302,8 +318,9 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     constexpr int NV = 2 * G3_TILE_BYTES / 16 / G3_CONV_THREADS;  // 8 x 16 bytes per thread per k block
     int s = 0;
     uint32_t ph = 0;
-    for (int64_t w = blockIdx.x; w < p.total; w += gridDim.x) {
-      const int nkb = g3_decode(p, w).nkb;
+    G3Work wk;
+    for (int64_t wi = 0; g3_decode(p, wi, wk); ++wi) {
+      const int nkb = wk.nkb;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(smem_u32(&full[s]), ph);
         const uint4* src = reinterpret_cast<const uint4*>(smem + s * G3_STAGE_BYTES) + ct;
@@ -479,6 +496,8 @@ extern "C" int lob_gemm3x(int64_t batch, int64_t M, int64_t N, int64_t K, const 
   p.tiles_n = (int)tiles_n;
   p.nbatch = batch;
   p.total = batch * splits * tiles_m * tiles_n;
+  p.jobs = batch * splits * tiles_n;
+  p.sched_flat = (tiles_m > 8 || p.jobs < kNumSMs) ? 1 : 0;
   p.splits = splits;
   p.kps = cdiv(cdiv(K, splits), G3_BK) * G3_BK;
   p.a_div = a_batch_div;
@@ -492,7 +511,7 @@ extern "C" int lob_gemm3x(int64_t batch, int64_t M, int64_t N, int64_t K, const 
     p.partial = (float*)ws;
   }
   LOB_CUDA(cudaFuncSetAttribute(k_gemm3x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G3_SMEM));
-  const unsigned grid = (unsigned)std::min<int64_t>(p.total, kNumSMs);
+  const unsigned grid = (unsigned)std::min<int64_t>(p.sched_flat ? p.total : p.jobs, kNumSMs);
   k_gemm3x<<<grid, G3_THREADS, G3_SMEM, st>>>(tmA, tmB, p);
   LOB_TRY(check_launch("k_gemm3x"));
   if (splits > 1) {

@@ -6,6 +6,7 @@ from .dense_linear_operator import DenseLinearOperator, to_linear_operator
 from .diag_linear_operator import ConstantDiagLinearOperator, DiagLinearOperator
 from .identity_linear_operator import IdentityLinearOperator
 from .kronecker_product_linear_operator import KroneckerProductLinearOperator
+from .kronecker_product_added_diag_linear_operator import KroneckerProductAddedDiagLinearOperator
 from .linear_operator_representation_tree import LinearOperatorRepresentationTree
 from .low_rank_root_added_diag_linear_operator import LowRankRootAddedDiagLinearOperator
 from .root_linear_operator import LowRankRootLinearOperator, RootLinearOperator
@@ -20,6 +21,7 @@ __all__ = [
     "DenseLinearOperator",
     "DiagLinearOperator",
     "IdentityLinearOperator",
+    "KroneckerProductAddedDiagLinearOperator",
     "KroneckerProductLinearOperator",
     "LinearOperator",
     "LinearOperatorRepresentationTree",

@@ -558,6 +558,130 @@ class LinearOperator(object):
             inv_quad_term = inv_quad_term.sum(-1)
         return inv_quad_term, logdet_term
 
+    # ------------------------------------------------------------------ Lanczos decompositions
+    def _root_decomposition_size(self) -> int:  # :715-721
+        return settings.max_root_decomposition_size.value()
+
+    def _choose_root_method(self) -> str:  # :543-561 (no decomposition caches on this path)
+        if self.size(-1) <= settings.max_cholesky_size.value() or settings.fast_computations.covar_root_decomposition.off():
+            return "cholesky"
+        return "lanczos"
+
+    def _root_decomposition(self):  # :689-713
+        from ..functions._root_decomposition import RootDecomposition
+
+        res, _ = RootDecomposition.apply(
+            self.representation_tree(), self._root_decomposition_size(), self.dtype, self.device, self.batch_shape,
+            self.matrix_shape, True, False, None, *self.representation(),
+        )
+        return res
+
+    def _root_inv_decomposition(self, initial_vectors=None, test_vectors=None):  # :723-761
+        from ..functions._root_decomposition import RootDecomposition
+
+        _, inv_roots = RootDecomposition.apply(
+            self.representation_tree(), self._root_decomposition_size(), self.dtype, self.device, self.batch_shape,
+            self.matrix_shape, True, True, initial_vectors, *self.representation(),
+        )
+        return inv_roots
+
+    def root_decomposition(self, method: Optional[str] = None) -> "LinearOperator":
+        """RootLinearOperator R with R R^T ~ A (reference :2158-2218).  Methods on this path: "lanczos" (default above
+        ``max_cholesky_size``), "cholesky", "pivoted_cholesky", "diagonalization"."""
+        from .root_linear_operator import RootLinearOperator
+
+        if not self.is_square:
+            raise RuntimeError(
+                "root_decomposition only operates on (batches of) square (symmetric) LinearOperators. "
+                "Got a {} of size {}.".format(self.__class__.__name__, self.size())
+            )
+        if self.shape[-2:].numel() == 1:
+            return RootLinearOperator(self.to_dense().sqrt())
+        if method is None:
+            method = self._choose_root_method()
+        if method == "cholesky":
+            return RootLinearOperator(self.cholesky())
+        if method == "pivoted_cholesky":
+            return RootLinearOperator(self.pivoted_cholesky(rank=self._root_decomposition_size()))
+        if method == "diagonalization":
+            evals, evecs = self.diagonalization()
+            return RootLinearOperator(evecs.to_dense() * evals.clamp_min(0.0).sqrt().unsqueeze(-2))
+        if method == "lanczos":
+            return RootLinearOperator(self._root_decomposition())
+        raise RuntimeError(f"Unknown root decomposition method '{method}'")
+
+    def root_inv_decomposition(self, initial_vectors=None, test_vectors=None, method: Optional[str] = None):
+        """RootLinearOperator R with R R^T ~ A^-1 (reference :2221-2310); "lanczos" with a single initial vector,
+        "cholesky" and "diagonalization" are on this path."""
+        from .root_linear_operator import RootLinearOperator
+
+        if not self.is_square:
+            raise RuntimeError(
+                "root_inv_decomposition only operates on (batches of) square (symmetric) LinearOperators. "
+                "Got a {} of size {}.".format(self.__class__.__name__, self.size())
+            )
+        if self.shape[-2:].numel() == 1:
+            return RootLinearOperator(1 / self.to_dense().sqrt())
+        if method is None:
+            method = self._choose_root_method()
+        if method == "cholesky":
+            L = self.cholesky()
+            eye = torch.eye(L.shape[-2], device=L.device, dtype=L.dtype)
+            return RootLinearOperator(torch.linalg.solve_triangular(L, eye, upper=False).mT)
+        if method == "lanczos":
+            if initial_vectors is not None:
+                if self.dim() == 2 and initial_vectors.dim() == 1:
+                    if self.shape[-1] != initial_vectors.numel():
+                        raise RuntimeError(
+                            "LinearOperator (size={}) cannot be multiplied with initial_vectors (size={}).".format(
+                                self.shape, initial_vectors.shape
+                            )
+                        )
+                elif self.dim() != initial_vectors.dim():
+                    raise RuntimeError(
+                        "LinearOperator (size={}) and initial_vectors (size={}) should have the same number "
+                        "of dimensions.".format(self.shape, initial_vectors.shape)
+                    )
+                elif self.batch_shape != initial_vectors.shape[:-2] or self.shape[-1] != initial_vectors.shape[-2]:
+                    raise RuntimeError(
+                        "LinearOperator (size={}) cannot be multiplied with initial_vectors (size={}).".format(
+                            self.shape, initial_vectors.shape
+                        )
+                    )
+                if initial_vectors.size(-1) > 1:
+                    raise NotImplementedError(
+                        "root_inv_decomposition with several initial vectors (test-vector selection, reference "
+                        ":2311-2350) is outside the Krylov path."
+                    )
+            return RootLinearOperator(self._root_inv_decomposition(initial_vectors))
+        if method == "diagonalization":
+            evals, evecs = self.diagonalization()
+            return RootLinearOperator(evecs.to_dense() * evals.clamp_min(1e-7).reciprocal().sqrt().unsqueeze(-2))
+        raise RuntimeError(f"Unknown root inv decomposition method '{method}'")
+
+    def diagonalization(self, method: Optional[str] = None):
+        """(eigenvalues (*b, k), eigenvectors as an operator (*b, N, k)) with Q S Q^T ~ A (reference :1439-1482)."""
+        from ..functions._diagonalization import Diagonalization
+        from .dense_linear_operator import to_linear_operator
+
+        if not self.is_square:
+            raise RuntimeError(
+                "diagonalization only operates on (batches of) square (symmetric) LinearOperators. "
+                "Got a {} of size {}.".format(self.__class__.__name__, self.size())
+            )
+        if method is None:
+            method = "symeig" if self.size(-1) <= settings.max_cholesky_size.value() else "lanczos"
+        if method == "lanczos":
+            evals, evecs = Diagonalization.apply(
+                self.representation_tree(), self.device, self.dtype, self.matrix_shape,
+                self._root_decomposition_size(), self.batch_shape, *self.representation(),
+            )
+            return evals, to_linear_operator(evecs)
+        if method == "symeig":  # small dense problems, off the Krylov path like the dense Cholesky branch
+            evals, evecs = torch.linalg.eigh(self.to_dense())
+            return evals, to_linear_operator(evecs)
+        raise RuntimeError(f"Unknown diagonalization method '{method}'")
+
     @_implements(torch.logdet)
     def logdet(self) -> Tensor:
         """log |A| (reference :1834-1842)."""
@@ -565,11 +689,21 @@ class LinearOperator(object):
         return res
 
     def zero_mean_mvn_samples(self, num_samples: int) -> Tensor:
-        """Samples from N(0, self): (num_samples, *batch, N).  Generic operators need a root decomposition (Lanczos),
-        which is a 'next' row; the classes used as ``precond_lt`` override this."""
-        raise NotImplementedError(
-            f"zero_mean_mvn_samples for {self.__class__.__name__} needs RootDecomposition (not on the built path)."
-        )
+        """Samples from N(0, self): (num_samples, *batch, N) = R eps with R the root decomposition (Lanczos above
+        ``max_cholesky_size``) and eps = randn(*batch, k, S)  (reference :2746-2793, non-CIQ branch)."""
+        if settings.ciq_samples.on():
+            raise NotImplementedError("settings.ciq_samples (contour-integral quadrature sampling) is not on this path.")
+        if self.size()[-2:] == torch.Size([1, 1]):
+            covar_root = self.to_dense().sqrt()
+        else:
+            covar_root = self.root_decomposition().root.to_dense()
+        base_samples = torch.randn(*self.batch_shape, covar_root.size(-1), num_samples, dtype=self.dtype,
+                                   device=self.device)
+        if covar_root.is_cuda:
+            samples = _kernels.matmul_nn(covar_root, base_samples)
+        else:
+            samples = covar_root.matmul(base_samples)
+        return samples.permute(-1, *range(self.dim() - 1)).contiguous()
 
     # ------------------------------------------------------------------ indexing (the subset the path needs)
     def __getitem__(self, index):

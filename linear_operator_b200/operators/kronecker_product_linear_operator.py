@@ -40,6 +40,38 @@ class KroneckerProductLinearOperator(LinearOperator):
         res = _kernels.kron_matmul(self._factor_tensors(), rhs)
         return res.squeeze(-1) if squeeze else res
 
+    def add_diagonal(self, diag):  # :116-150
+        from .diag_linear_operator import ConstantDiagLinearOperator, DiagLinearOperator
+        from .kronecker_product_added_diag_linear_operator import KroneckerProductAddedDiagLinearOperator
+
+        if not self.is_square:
+            raise RuntimeError("add_diag only defined for square matrices")
+        if diag.dim() == 0:
+            diag_op = ConstantDiagLinearOperator(diag.unsqueeze(-1), diag_shape=self.shape[-1])
+        elif diag.shape[-1] == 1:
+            diag_op = ConstantDiagLinearOperator(diag, diag_shape=self.shape[-1])
+        else:
+            try:
+                expanded = diag.expand(self.shape[:-1])
+            except RuntimeError:
+                raise RuntimeError(
+                    "add_diagonal for LinearOperator of size {} received invalid diagonal of size {}.".format(
+                        self.shape, diag.shape
+                    )
+                ) from None
+            diag_op = DiagLinearOperator(expanded)
+        return KroneckerProductAddedDiagLinearOperator(self, diag_op)
+
+    def __add__(self, other):  # :98-114
+        from .diag_linear_operator import ConstantDiagLinearOperator, DiagLinearOperator
+        from .kronecker_product_added_diag_linear_operator import KroneckerProductAddedDiagLinearOperator
+
+        if isinstance(other, ConstantDiagLinearOperator):
+            return KroneckerProductAddedDiagLinearOperator(self, other)
+        if isinstance(other, DiagLinearOperator):
+            return self.add_diagonal(other._diagonal())
+        return super().__add__(other)
+
     def _matmul_add_diag(self, rhs, diag):
         """K X + d (.) X with the diagonal folded into the chain's last pass (AddedDiagLinearOperator._matmul)."""
         return _kernels.kron_matmul(self._factor_tensors(), rhs, d=diag)

@@ -88,10 +88,8 @@ class LowRankRootAddedDiagLinearOperator(AddedDiagLinearOperator):
                 w = w[0]
             w, _, _ = _kernels.cap_solve(self._gram().reshape(-1, k, k), w.unsqueeze(-1))
             w = w.squeeze(-1)  # (B, k)
-            # x^T (N x B) = U w^T with N as the GEMM's M (lane) index and the result stored transposed, i.e. as (B, N):
-            # every epilogue load of R and store of x is a full line although the rows of R / x are 4 N bytes apart
-            x = _kernels.gemm3x(U.unsqueeze(0), w.unsqueeze(0), trans_b=True, row_alpha=(-inv_sig).unsqueeze(0),
-                                E=R.unsqueeze(0), row_beta=inv_sig.unsqueeze(0), store_transposed=True)
+            x = _kernels.gemm3x(w.unsqueeze(0), U.unsqueeze(0), trans_b=True, row_alpha=(-inv_sig).unsqueeze(0),
+                                E=R.unsqueeze(0), row_beta=inv_sig.unsqueeze(0))
             if x is None:
                 S = _kernels.matmul_nn(U.unsqueeze(0), w.mT.unsqueeze(0))[0].mT  # (B, N) = (U w^T)^T
                 x = (R - S) * inv_sig.unsqueeze(-1)

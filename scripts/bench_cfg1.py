@@ -43,18 +43,45 @@ def sync():
         torch.cuda.synchronize()
 
 
-with settings.max_cholesky_size(0), settings.num_trace_samples(16), torch.no_grad():
+def measure(reps=50):
     for _ in range(5):
-        iq, ld = step()
+        step()
     sync()
     t0 = time.perf_counter()
-    reps = 50
     for _ in range(reps):
-        iq, ld = step()
+        out = step()
     sync()
-    dt = (time.perf_counter() - t0) / reps
+    return out, (time.perf_counter() - t0) / reps
+
+
+extra = {}
+with settings.max_cholesky_size(0), settings.num_trace_samples(16), torch.no_grad():
+    (iq, ld), dt = measure()
+    if impl == "ours":
+        with settings.cuda_graphs(False):
+            _, dt_eager = measure()
+        extra = {"ms_per_call_without_cuda_graph": dt_eager * 1e3, "calls_per_s_without_cuda_graph": 1 / dt_eager}
+        # the solver alone (21 iterations, 17 columns), graph replay vs launch by launch
+        from linear_operator_b200.utils import linear_cg
+
+        op = AddedDiagLinearOperator(DenseLinearOperator(K), DiagLinearOperator(d))
+        rhs17 = torch.randn(1, N, 17, device=dev, generator=g, dtype=torch.float64)
+
+        def solve():
+            return linear_cg(op._matmul_closure(), rhs17, n_tridiag=16, _skip_initial_matmul=True)
+
+        for flag in (True, False):
+            with settings.cuda_graphs(flag):
+                for _ in range(5):
+                    solve()
+                sync()
+                t0 = time.perf_counter()
+                for _ in range(50):
+                    solve()
+                sync()
+                extra["linear_cg_ms_graph" if flag else "linear_cg_ms_eager"] = (time.perf_counter() - t0) / 50 * 1e3
 exact = torch.logdet(K[0] + torch.diag(d[0]))
 print(json.dumps({"config": "BASELINE configs[0]: Dense+AddedDiag N=512 batch 1 fp64 16 probes, cold calls", "impl": impl,
                   "device": str(dev), "calls_per_s": 1 / dt, "ms_per_call": dt * 1e3, "cg_iters_per_s": 21 / dt,
                   "logdet": float(ld), "logdet_exact": float(exact),
-                  "threads": torch.get_num_threads() if dev.type == "cpu" else None}))
+                  "threads": torch.get_num_threads() if dev.type == "cpu" else None, **extra}))

@@ -40,8 +40,8 @@ for splits in (37, 1024, 0):
                       "relerr_vs_fp64": err}), flush=True)
 wc = torch.randn(B, r, device=dev, generator=g) / 100
 sig = 0.5 + torch.rand(B, device=dev, generator=g)
-x, ms = timed(lambda: _kernels.gemm3x(U.unsqueeze(0), wc.unsqueeze(0), trans_b=True, row_alpha=(-1 / sig).unsqueeze(0),
-                                      E=R.unsqueeze(0), row_beta=(1 / sig).unsqueeze(0), store_transposed=True))
+x, ms = timed(lambda: _kernels.gemm3x(wc.unsqueeze(0), U.unsqueeze(0), trans_b=True, row_alpha=(-1 / sig).unsqueeze(0),
+                                      E=R.unsqueeze(0), row_beta=(1 / sig).unsqueeze(0)))
 x_ref = (R[:16].double() - wc[:16].double() @ Ud.mT) / sig[:16].double().unsqueeze(-1)
 alg = 4.0 * (2 * B * N + N * r)
 print(json.dumps({"product": "x = (R - w U^T) / sigma  (B x r)(r x N), fused epilogue", "ms": ms, "GBps": alg / ms / 1e6,

@@ -279,8 +279,9 @@ def test_cuda_graph_replay_is_bit_identical_to_eager_launches():
     """BASELINE configs[0]-sized problems are launch-bound; linear_cg replays the fixed-length part of the solve as one
     CUDA graph on static buffers.  Same kernels, same order: the results must not differ by a bit, also when the graph
     is replayed on new data and when the stop rule only fires after the captured part."""
-    from linear_operator_b200.utils import linear_cg as cg_module  # noqa: F401
-    import linear_operator_b200.utils.linear_cg as cgm
+    import sys
+
+    cgm = sys.modules["linear_operator_b200.utils.linear_cg"]  # (the package re-exports the function under this name)
 
     gen = torch.Generator(device=DEV).manual_seed(17)
     n, s = 512, 16
@@ -309,3 +310,40 @@ def test_cuda_graph_replay_is_bit_identical_to_eager_launches():
         for (a, b, c), (a2, b2, c2) in zip(eager, replayed):
             assert torch.equal(a, a2) and torch.equal(b, b2) and torch.equal(c, c2)
     del gen
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Kronecker + constant diagonal through the Kronecker eigenbasis
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,rtol", [("kron_added_diag_f64", F64_RTOL), ("kron_added_diag_f32", F32_RTOL)])
+def test_kronecker_added_diag_eigen_path_vs_reference(golden, name, rtol):
+    from linear_operator_b200.operators import KroneckerProductAddedDiagLinearOperator
+
+    g = golden(name)
+    op = KroneckerProductLinearOperator(cu(g["f0"]), cu(g["f1"]), cu(g["f2"])).add_jitter(float(g["jitter"]))
+    assert type(op) is KroneckerProductAddedDiagLinearOperator and op._preconditioner() == (None, None, None)
+    rhs = cu(g["rhs"])
+    with settings.max_cholesky_size(0):
+        sol = op.solve(rhs)
+        iq, ld = op.inv_quad_logdet(rhs, logdet=True)
+        ld_only = torch.logdet(op)
+    assert sol.dtype == rhs.dtype and ld.dtype == rhs.dtype
+    check(npy(sol), g["solve"], rtol)
+    check(npy(iq), g["inv_quad"], rtol)
+    check(npy(ld), g["logdet"], rtol)
+    check(npy(ld_only), g["logdet_only"], rtol)
+
+
+def test_kronecker_added_diag_eigen_path_mid_size_vs_dense():
+    """20 x 20 x 20 (N = 8000, the tensor-core chain's alignment) in fp32, against a dense fp64 solve."""
+    gen = torch.Generator(device=DEV).manual_seed(44)
+    fs = []
+    for _ in range(3):
+        G = torch.randn(20, 20, device=DEV, generator=gen)
+        fs.append(G @ G.mT / 20 + 0.1 * torch.eye(20, device=DEV))
+    op = KroneckerProductLinearOperator(*fs).add_jitter(0.3)
+    rhs = torch.randn(8000, 4, device=DEV, generator=gen)
+    sol = op.solve(rhs)
+    dense = torch.kron(torch.kron(fs[0].double(), fs[1].double()), fs[2].double()) + 0.3 * torch.eye(8000, device=DEV, dtype=torch.float64)
+    check(npy(sol), npy(torch.linalg.solve(dense, rhs.double())), F32_RTOL)
+    check(npy(op.logdet()), npy(torch.logdet(dense)), F32_RTOL)
