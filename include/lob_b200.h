@@ -121,6 +121,12 @@ int lob_dense_matmul(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, 
                      int64_t a_batch_stride, const void* X, void* Y, const void* d, int64_t d_batch_stride,
                      int64_t d_stride, double* dots, void* ws, size_t ws_bytes, void* stream);
 
+/* Test hook: pins the fp32 dense-matmul implementation (0 automatic dispatch, 1 dense_stream2, 2 dense_stream,
+ * 3 dense_tc, 4 CUDA cores) so the tests can compare the kernels with each other on the same call.  Every choice
+ * computes the same product to fp32 accuracy; nothing in the release library changes numerics through the environment
+ * (the harness-only experiment switches of the streaming kernels exist only when compiled with -DLOB_DIAG). */
+int lob_debug_pin_dense_impl(int32_t impl);
+
 /* Generalised epilogue:  Y = alpha[b] * (A X) + d (.) E,  dots = per-row-tile partial sums of E * Y.
  * E (B, M, C) may be NULL (then E = X, which needs M == K); alpha (one value per batch element, stride
  * alpha_batch_stride) may be NULL (= 1).  With A = Q, X = Q^T r, E = r, alpha = -1/s, d = 1/s this is the whole

@@ -389,7 +389,16 @@ class AddedDiagPreconditioner:
         else:
             self.noise = diag.expand(*self.batch_shape, N).reshape(B, N).contiguous()
             Ls = scale_rows(L, self.noise.reshape(*self.batch_shape, N), "div_sqrt")  # D^-1/2 L (:176-178)
-        G = tn_matmul(Ls, Ls, out_dtype=torch.float64).reshape(B, k, k)
+        # Gram matrix L^T L (k x k, contraction over N) in double.  fp32 factors: tensor cores with split-K so that no
+        # accumulator sees more than 512 contraction indices (the truncating fp32 accumulate would otherwise bias the
+        # all-positive diagonal sums by ~1.5e-8 per index), partial sums added in double; fp64 factors: CUDA cores.
+        G = None
+        if dty == torch.float32 and N >= 2048:
+            G = gemm3x(Ls.reshape(B, N, k), Ls.reshape(B, N, k), trans_a=True, splits=max(2, -(-N // 512)),
+                       out_dtype=torch.float64)
+        if G is None:
+            G = tn_matmul(Ls, Ls, out_dtype=torch.float64)
+        G = G.reshape(B, k, k)
         rinv = torch.empty(B, k, k, dtype=dty, device=dev)
         logdet_r = torch.empty(B, dtype=dty, device=dev)
         info = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -399,7 +408,9 @@ class AddedDiagPreconditioner:
                                    ptr(logdet_r), ptr(info), ptr(ws), stream(L)),
             "lob_precond_factor",
         )
-        Q = matmul_nn(Ls.reshape(B, N, k), rinv)  # Q1 = L R^-1
+        Q = gemm3x(Ls.reshape(B, N, k), rinv) if dty == torch.float32 and N >= 2048 else None  # Q1 = L R^-1
+        if Q is None:
+            Q = matmul_nn(Ls.reshape(B, N, k), rinv)
         if constant:
             self.Q = Q
             # logdet M = 2 sum log|R_ii| + (N - k) log s   (:170-172); tiny (B,) op on the control path

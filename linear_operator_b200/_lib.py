@@ -67,6 +67,7 @@ _SIGS = {
     "lob_cg_step_p": (ctypes.c_int, [POINTER(CgParams), _P, c_int32, _P, _P, _P, _P, _P, c_int32, _P]),
     "lob_cg_poll_sync": (ctypes.c_int, [POINTER(CgParams), _P, POINTER(CgStatus), _P]),
     "lob_cg_finish": (ctypes.c_int, [POINTER(CgParams), _P, _P, _P]),
+    "lob_debug_pin_dense_impl": (ctypes.c_int, [c_int32]),
     "lob_dense_matmul_parts": (c_int32, [c_int64]),
     "lob_dense_matmul_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64, c_int64, c_int64]),
     "lob_dense_matmul": (
@@ -182,6 +183,14 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+_DENSE_IMPLS = {None: 0, "auto": 0, "stream2": 1, "stream": 2, "tc": 3, "simt": 4}
+
+
+def pin_dense_impl(name=None):
+    """Test hook: pins the fp32 dense-matmul kernel ("stream2", "stream", "tc", "simt"; None = automatic dispatch)."""
+    check(load().lob_debug_pin_dense_impl(_DENSE_IMPLS[name]), "lob_debug_pin_dense_impl")
 
 
 def launch_count() -> int:

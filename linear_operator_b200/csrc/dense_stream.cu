@@ -366,11 +366,13 @@ struct DsConfig {
 static DsConfig ds_default_config() {
   static DsConfig cfg = [] {
     DsConfig c{16, 0, 0, 0, 0, 0};
+#ifdef LOB_DIAG  // tuning / bottleneck-experiment knobs exist only in the harness build
     if (const char* e = getenv("LOB_DS_BK")) c.bk = atoi(e);
     if (const char* e = getenv("LOB_DS_SA")) c.sa = atoi(e);
     if (const char* e = getenv("LOB_DS_SL")) c.sl = atoi(e);
     if (const char* e = getenv("LOB_DS_LO")) c.lo_mode = atoi(e);
     if (const char* e = getenv("LOB_DS_GRID")) c.grid = atoi(e);
+#endif
     return c;
   }();
   return cfg;

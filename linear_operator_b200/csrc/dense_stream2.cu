@@ -483,12 +483,14 @@ struct D2Config {
 static D2Config d2_default_config() {
   static D2Config cfg = [] {
     D2Config c{0, 32, 0, 0, 0, 0};
+#ifdef LOB_DIAG  // tuning / bottleneck-experiment knobs exist only in the harness build
     if (const char* e = getenv("LOB_D2_ACC_BUFS")) c.acc_bufs = atoi(e);
     if (const char* e = getenv("LOB_D2_XMODE")) c.xmode = atoi(e);
     if (const char* e = getenv("LOB_D2_DBG")) c.dbg = atoi(e);
     if (const char* e = getenv("LOB_D2_BK")) c.bk = atoi(e);
     if (const char* e = getenv("LOB_D2_SA")) c.sa = atoi(e);
     if (const char* e = getenv("LOB_D2_GRID")) c.grid = atoi(e);
+#endif
     return c;
   }();
   return cfg;

@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <type_traits>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "simt_tile.cuh"
 
@@ -248,7 +250,7 @@ static int launch_tn(int64_t B, int64_t N, int64_t I, int64_t J, const T* P, int
   TnPlan p = tn_plan(B, N, I, J);
   ACC* partial = (ACC*)ws;
   if constexpr (std::is_same<T, float>::value && std::is_same<ACC, float>::value) {
-    if (!getenv("LOB_DISABLE_TN_SKINNY") && tn_skinny_applicable(N, I, J, P, p_bs)) {
+    if (tn_skinny_applicable(N, I, J, P, p_bs)) {
       // the workspace is sized for max(generic plan, skinny plan) splits (lob_tn_matmul_workspace_bytes)
       const int ns = tn_skinny_nsplit(B, N);
       int s = launch_tn_skinny_f32(B, N, I, J, P, p_bs, Q, q_bs, partial, ns, st);
@@ -311,47 +313,40 @@ int dense_matmul_stream2_f32(int64_t B, int64_t M, int64_t K, int64_t C, const f
                              const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
                              cudaStream_t st);
 
-// nn_skinny.cu: CUDA-core kernel for short contractions (K <= 160, C <= 40) with the fused epilogue
-bool nn_skinny_applicable(int64_t M, int64_t K, int64_t C, const void* A, int64_t lda, int64_t a_bs);
-int launch_nn_skinny_f32(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
-                         const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs, const float* d,
-                         int64_t d_bs, int64_t d_st, double* dots, cudaStream_t st);
-
 // fp32 dispatch: streaming tcgen05 kernels (need the workspace; dense_stream2.cu for C <= 48, dense_stream.cu up to
 // C = 64) -> first-generation tcgen05 kernel -> CUDA cores.
-// LOB_DENSE_IMPL = stream2 | stream | nnskinny | tc | simt pins one of them (diagnostics, A/B comparisons).
+// lob_debug_pin_dense_impl() pins one of them (A/B comparisons in the tests; every choice computes the same product).
+static std::atomic<int> g_dense_pin{0};  // 0 auto, 1 stream2, 2 stream, 3 tc, 4 simt
 static int dense_f32_tensor_paths(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
                                   const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
                                   const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
                                   cudaStream_t st) {
-  const char* impl = getenv("LOB_DENSE_IMPL");
-  if (getenv("LOB_DISABLE_TC") || (impl && !strcmp(impl, "simt"))) return LOB_ERR_UNSUPPORTED;
+  const int pin = g_dense_pin.load(std::memory_order_relaxed);
+  const bool impl = pin != 0;
+  if (pin == 4) return LOB_ERR_UNSUPPORTED;
   // dense_stream2 serves long contractions (streaming regime) and short ones (K <= 256: the preconditioner product
   // Q t with the fused z, <r,z> epilogue -- 1.62 ms at config 2 since its epilogue reduces the fp64 partials with a
   // transpose-reduce, against 2.25 ms for the first-generation kernel); the window in between stays on the older kernel.
-  const bool pinned_stream2 = impl && !strcmp(impl, "stream2");
+  const bool pinned_stream2 = pin == 1;
   if (pinned_stream2 || (!impl && (K >= 512 || (K <= 256 && a_bs != 0)))) {
     int s = dense_matmul_stream2_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, ws,
                                      ws_bytes, st);
     if (s != LOB_ERR_UNSUPPORTED) return s;
   }
-  const bool pinned_stream = impl && !strcmp(impl, "stream");
+  const bool pinned_stream = pin == 2;
   if (pinned_stream || (!impl && K >= 512)) {
     int s = dense_matmul_stream_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, ws,
                                     ws_bytes, st);
     if (s != LOB_ERR_UNSUPPORTED) return s;
   }
-  // short contractions (the preconditioner's Q t with the fused z, <r,z> epilogue): one-tile CUDA-core kernel.  Measured
-  // 2.8 - 3.3 ms at config 2 against 2.25 ms for the first-generation tensor-core kernel below, so it only runs when
-  // pinned (LOB_DENSE_IMPL=nnskinny); kept as the tested CUDA-core alternative for this shape.
-  const bool pinned_skinny = impl && !strcmp(impl, "nnskinny");
-  if (pinned_skinny && a_bs != 0 && nn_skinny_applicable(M, K, C, A, lda, a_bs) &&
-      !((d || dots) && !E && M != K)) {
-    int s = launch_nn_skinny_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, st);
-    if (s != LOB_ERR_UNSUPPORTED) return s;
-  }
   return dense_matmul_tc_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, st);
 }
+}
+
+extern "C" int lob_debug_pin_dense_impl(int32_t impl) {
+  LOB_REQUIRE(impl >= 0 && impl <= 4, "lob_debug_pin_dense_impl: 0 auto, 1 stream2, 2 stream, 3 tc, 4 simt");
+  lob::g_dense_pin.store(impl);
+  return LOB_OK;
 }
 
 extern "C" size_t lob_dense_matmul_workspace_bytes(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C) {

@@ -33,7 +33,7 @@ static PcLayout pc_layout(int64_t B, int64_t N, int rank, size_t es) {
   if (nch > maxch) nch = maxch;
   if (nch > 256) nch = 256;
   if (nch < 1) nch = 1;
-  L.cols_per_chunk = cdiv(N, nch);
+  L.cols_per_chunk = cdiv(cdiv(N, nch), 4) * 4;  // multiple of 4: lets the fp32 update use 16-byte words
   L.nchunks = (int)cdiv(N, L.cols_per_chunk);
   size_t o = 0;
   auto take = [&](size_t bytes) {
@@ -320,6 +320,94 @@ k_pc_update(Src src, int64_t N, int rankmax, int m, int nchunks, int64_t cpc, T*
   }
 }
 
+// fp32 variant with four consecutive columns per thread (N % 4 == 0): every load of a previous row of L is a 16-byte
+// word and a CTA touches 4 KB of it at a time instead of 1 KB -- the update reads m rows of N floats per step, each
+// 4 N bytes apart, so longer contiguous runs are what the DRAM pages want.  Arithmetic and its order per column are
+// those of k_pc_update (one rounding per multiply and per add), candidates are merged in the same order.
+template <typename Src>
+__global__ void __launch_bounds__(256)
+k_pc_update_v4(Src src, int64_t N, int rankmax, int m, int nchunks, int64_t cpc, float* __restrict__ diag,
+               const int* __restrict__ pos, const int* __restrict__ pi, const float* __restrict__ piv,
+               float* __restrict__ Lt, float* __restrict__ cval, int* __restrict__ cpos, int* __restrict__ cidx,
+               double* __restrict__ errsum, const PcControl* ctrl) {
+  extern __shared__ unsigned char smem_raw[];
+  float* u = reinterpret_cast<float*>(smem_raw);
+  __shared__ float sv[32];
+  __shared__ int sp[32], si[32];
+  __shared__ double scratch[32];
+  if (!ctrl->active || ctrl->m != m + 1) return;
+  const int64_t b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int64_t i0 = (int64_t)chunk * cpc, i1 = min(i0 + cpc, N);  // cpc % 4 == 0
+  const int64_t r = pi[b];
+  const float pv = piv[b];
+  float* Lb = Lt + b * rankmax * N;
+  for (int t = threadIdx.x; t < m; t += blockDim.x) u[t] = Lb[(int64_t)t * N + r];
+  __syncthreads();
+  float bv = 0.f;
+  int bp = -1, bi = -1;
+  double es = 0.0;
+  for (int64_t i = i0 + 4 * (int64_t)threadIdx.x; i < i1; i += 4 * (int64_t)blockDim.x) {
+    const int4 p4 = *reinterpret_cast<const int4*>(pos + b * N + i);
+    const int pp[4] = {p4.x, p4.y, p4.z, p4.w};
+    if (pp[0] <= m && pp[1] <= m && pp[2] <= m && pp[3] <= m) continue;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    int t = 0;
+    for (; t + 3 < m; t += 4) {
+      float4 l[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) l[q] = *reinterpret_cast<const float4*>(Lb + (int64_t)(t + q) * N + i);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float uq = u[t + q];
+        s[0] = __fadd_rn(s[0], __fmul_rn(uq, l[q].x));
+        s[1] = __fadd_rn(s[1], __fmul_rn(uq, l[q].y));
+        s[2] = __fadd_rn(s[2], __fmul_rn(uq, l[q].z));
+        s[3] = __fadd_rn(s[3], __fmul_rn(uq, l[q].w));
+      }
+    }
+    for (; t < m; ++t) {
+      const float4 l0 = *reinterpret_cast<const float4*>(Lb + (int64_t)t * N + i);
+      const float uq = u[t];
+      s[0] = __fadd_rn(s[0], __fmul_rn(uq, l0.x));
+      s[1] = __fadd_rn(s[1], __fmul_rn(uq, l0.y));
+      s[2] = __fadd_rn(s[2], __fmul_rn(uq, l0.z));
+      s[3] = __fadd_rn(s[3], __fmul_rn(uq, l0.w));
+    }
+    float4 d4 = *reinterpret_cast<const float4*>(diag + b * N + i);
+    float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+    float out[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      out[q] = 0.f;
+      if (pp[q] <= m) {  // already pivoted: leave L and diag as they are
+        out[q] = Lb[(int64_t)m * N + i + q];
+        continue;
+      }
+      float v = src.entry(b, r, i + q);
+      if (m > 0) v = v - s[q];
+      v = v / pv;
+      out[q] = v;
+      const float dn = dd[q] - __fmul_rn(v, v);
+      dd[q] = dn;
+      es += fabs((double)dn);
+      if (cand_better<float>(dn, pp[q], bv, bp)) {
+        bv = dn; bp = pp[q]; bi = (int)(i + q);
+      }
+    }
+    *reinterpret_cast<float4*>(Lb + (int64_t)m * N + i) = make_float4(out[0], out[1], out[2], out[3]);
+    *reinterpret_cast<float4*>(diag + b * N + i) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+  }
+  block_argmax<float>(bv, bp, bi, sv, sp, si);
+  const double tot = block_sum(es, scratch);
+  if (threadIdx.x == 0) {
+    cval[b * nchunks + chunk] = bv;
+    cpos[b * nchunks + chunk] = bp;
+    cidx[b * nchunks + chunk] = bi;
+    errsum[b * nchunks + chunk] = tot;
+  }
+}
+
 __global__ void k_pc_finish(const PcControl* ctrl, int32_t* m_out) { *m_out = ctrl->m; }
 __global__ void k_pc_status(const PcControl* ctrl, int32_t* m_out, int32_t* active_out) {
   *m_out = ctrl->m;
@@ -355,9 +443,22 @@ static int run_pivchol(Src src, int64_t B, int64_t N, int rank, double tol, T* L
                                       piv, Lt, ctrl);
     LOB_TRY(check_launch("k_pc_pivot"));
     if (m + 1 < N) {  // :77
-      k_pc_update<T, Src><<<grid, 256, sizeof(T) * (size_t)(rankmax > 0 ? rankmax : 1), st>>>(
-          src, N, rankmax, m, L.nchunks, L.cols_per_chunk, diag, pos, pi, piv, Lt, cval, cpos, cidx, errsum, ctrl);
-      LOB_TRY(check_launch("k_pc_update"));
+      bool done = false;
+      if constexpr (sizeof(T) == 4) {
+        if ((N % 4) == 0 && (L.cols_per_chunk % 4) == 0 && (reinterpret_cast<uintptr_t>(Lt) & 15) == 0 &&
+            (reinterpret_cast<uintptr_t>(diag) & 15) == 0 && (reinterpret_cast<uintptr_t>(pos) & 15) == 0) {
+          k_pc_update_v4<Src><<<grid, 256, sizeof(float) * (size_t)rankmax, st>>>(
+              src, N, rankmax, m, L.nchunks, L.cols_per_chunk, (float*)diag, pos, pi, (const float*)piv, (float*)Lt,
+              (float*)cval, cpos, cidx, errsum, ctrl);
+          LOB_TRY(check_launch("k_pc_update_v4"));
+          done = true;
+        }
+      }
+      if (!done) {
+        k_pc_update<T, Src><<<grid, 256, sizeof(T) * (size_t)(rankmax > 0 ? rankmax : 1), st>>>(
+            src, N, rankmax, m, L.nchunks, L.cols_per_chunk, diag, pos, pi, piv, Lt, cval, cpos, cidx, errsum, ctrl);
+        LOB_TRY(check_launch("k_pc_update"));
+      }
     }
   }
   k_pc_finish<<<1, 1, 0, st>>>(ctrl, m_out);

@@ -200,6 +200,13 @@ class deterministic_probes(_Flag):
     probe_vectors = None
 
 
+class ciq_samples(_Flag):
+    """Contour-integral-quadrature sampling (reference settings.py ciq_samples); default off.  The CIQ / MINRES route is
+    not on the built path: turning it on makes ``zero_mean_mvn_samples`` raise NotImplementedError."""
+
+    _default = False
+
+
 class cuda_graphs(_Flag):
     """Not in the reference.  Small dense problems (the operator at most ``cuda_graphs.max_operator_bytes``) are
     launch-bound: ~90 kernel launches for a 21-iteration solve of N = 512.  With this flag on (default) linear_cg
@@ -291,5 +298,5 @@ __all__ = [
     "max_preconditioner_size", "min_preconditioning_size", "preconditioner_tolerance", "num_trace_samples",
     "max_root_decomposition_size", "max_lanczos_iterations", "terminate_cg_by_size", "skip_logdet_forward",
     "deterministic_probes", "debug", "memory_efficient", "trace_mode", "verbose_linalg", "fast_computations",
-    "cholesky_jitter", "cholesky_max_tries", "tridiagonal_jitter",
+    "cholesky_jitter", "cholesky_max_tries", "tridiagonal_jitter", "ciq_samples", "cuda_graphs",
 ]

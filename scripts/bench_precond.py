@@ -1,12 +1,12 @@
 """Times the two products of the preconditioner apply z = (r - Q Q^T r)/s at config-2 shapes (B x 5000 x 100, 33 columns)
-through each dense kernel (LOB_DENSE_IMPL) and the CUDA-core Q^T r kernel.  Usage: python scripts/bench_precond.py [B]"""
+through each dense kernel (pinned with _lib.pin_dense_impl) and the CUDA-core Q^T r kernel.  Usage: python scripts/bench_precond.py [B]"""
 import os
 import sys
 
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from linear_operator_b200 import _kernels  # noqa: E402
+from linear_operator_b200 import _kernels, _lib  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 N, k, C = 5000, 100, 33
@@ -32,14 +32,14 @@ def timeit(fn, reps=10):
 
 
 ref = None
-for impl in ["tc", "nnskinny", "stream2", "simt"]:
-    os.environ["LOB_DENSE_IMPL"] = impl
+for impl in ["tc", "stream2", "simt"]:
+    _lib.pin_dense_impl(impl)
     ms = timeit(lambda: _kernels.dense_matmul(Q, t, d=d, want_dots=True, E=r, alpha=alpha))
     z = _kernels.dense_matmul(Q, t, d=d, want_dots=True, E=r, alpha=alpha)[0]
     if ref is None:
         ref = (alpha.view(B, 1, 1).double() * (Q.double() @ t.double()) + 2.0 * r.double())
     err = ((z.double() - ref).abs().max() / ref.abs().max()).item()
     print(f"Q t + epilogue  impl={impl:8s} B={B}: {ms:7.3f} ms   err {err:.2e}")
-del os.environ["LOB_DENSE_IMPL"]
+_lib.pin_dense_impl(None)
 ms = timeit(lambda: _kernels.tn_matmul(Q, r))
 print(f"Q^T r (tn_matmul, CUDA cores)   B={B}: {ms:7.3f} ms")
