@@ -331,6 +331,26 @@ int lob_toeplitz_cross_spectrum(int32_t dtype, int64_t B, int64_t C, int64_t H, 
 int lob_toeplitz_deriv_finish(int32_t dtype, int64_t B, int64_t N, int64_t L, const void* y, double scale, void* out,
                               void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Shifted MINRES (utils/minres.py:10-282), the solver of contour-integral quadrature (utils/contour_integral_quad.py).
+ * Vectors are (B, N, C), per-column scalars (B, C), per-shift scalars (Q, B, C), shifts (Q, B), search directions and
+ * solutions (Q, B, N, C).  One iteration = operator closure + 2 x lob_col_dots + these three launches:
+ *   lob_minres_z        prod <- prod - alpha z_prev1 - beta_prev z_prev2                         (minres.py:137)
+ *   lob_minres_scalars  beta_curr = max(sqrt(beta_sq), eps) and the Givens / QR recurrences per shift (:141-142,:231-245)
+ *   lob_minres_update   z /= beta_curr, q /= beta_curr (skipped when q == z), search_curr, solution += ... (:146-147,:246-251)
+ * ---------------------------------------------------------------------------------------------------------- */
+int lob_minres_z(int32_t dtype, int64_t B, int64_t N, int64_t C, void* prod, const void* z1, const void* z2,
+                 const void* alpha, const void* beta_prev, void* stream);
+int lob_minres_scalars(int32_t dtype, int64_t Q, int64_t B, int64_t C, const void* shifts, const void* alpha,
+                       const void* beta_prev, const void* beta_sq, void* beta_curr, const void* cos_prev2,
+                       const void* sin_prev2, const void* cos_prev1, const void* sin_prev1, void* cos_curr, void* sin_curr,
+                       void* scale_prev, void* scale_curr, void* sub_diag, void* subsub_diag, void* diag, double eps,
+                       void* stream);
+int lob_minres_update(int32_t dtype, int64_t Q, int64_t B, int64_t N, int64_t C, void* z, void* q, const void* beta_curr,
+                      const void* q_prev1, const void* search_prev1, const void* search_prev2, void* search_curr,
+                      void* solution, const void* sub_diag, const void* subsub_diag, const void* diag,
+                      const void* scale_prev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

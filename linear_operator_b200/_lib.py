@@ -159,6 +159,15 @@ _SIGS = {
     "lob_tri_inverse": (ctypes.c_int, [c_int32, c_int64, c_int32, _P, c_int64, c_int64, _P, _P]),
     "lob_toeplitz_cross_spectrum": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "lob_toeplitz_deriv_finish": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, c_double, _P, _P]),
+    "lob_minres_z": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
+    "lob_minres_scalars": (
+        ctypes.c_int,
+        [c_int32, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_double, _P],
+    ),
+    "lob_minres_update": (
+        ctypes.c_int,
+        [c_int32, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    ),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -691,8 +691,13 @@ class LinearOperator(object):
     def zero_mean_mvn_samples(self, num_samples: int) -> Tensor:
         """Samples from N(0, self): (num_samples, *batch, N) = R eps with R the root decomposition (Lanczos above
         ``max_cholesky_size``) and eps = randn(*batch, k, S)  (reference :2746-2793, non-CIQ branch)."""
-        if settings.ciq_samples.on():
-            raise NotImplementedError("settings.ciq_samples (contour-integral quadrature sampling) is not on this path.")
+        if settings.ciq_samples.on():  # :2758-2777: K^{1/2} eps through contour-integral quadrature + shifted MINRES
+            base_samples = torch.randn(*self.batch_shape, self.size(-1), num_samples, dtype=self.dtype,
+                                       device=self.device)
+            base_samples = base_samples.permute(-1, *range(self.dim() - 1)).contiguous().unsqueeze(-1)
+            solves, weights, _, _ = utils.contour_integral_quad(
+                self, base_samples, inverse=False, num_contour_quadrature=settings.num_contour_quadrature.value())
+            return (solves * weights).sum(0).squeeze(-1)
         if self.size()[-2:] == torch.Size([1, 1]):
             covar_root = self.to_dense().sqrt()
         else:

@@ -129,6 +129,18 @@ class cg_tolerance(_Value):
     _global_value = 1
 
 
+class minres_tolerance(_Value):
+    """Relative update-term tolerance that terminates MINRES; default 1e-4 (reference settings.py:464-471)."""
+
+    _global_value = 1e-4
+
+
+class num_contour_quadrature(_Value):
+    """Number of quadrature points of contour-integral quadrature; default 15 (reference settings.py:474-481)."""
+
+    _global_value = 15
+
+
 class max_cg_iterations(_Value):
     """Maximum CG iterations; default 1000 (:383-391)."""
 
@@ -201,8 +213,8 @@ class deterministic_probes(_Flag):
 
 
 class ciq_samples(_Flag):
-    """Contour-integral-quadrature sampling (reference settings.py ciq_samples); default off.  The CIQ / MINRES route is
-    not on the built path: turning it on makes ``zero_mean_mvn_samples`` raise NotImplementedError."""
+    """Contour-integral-quadrature sampling in ``zero_mean_mvn_samples`` (reference settings.py ciq_samples); default
+    off (samples come from the Lanczos root decomposition)."""
 
     _default = False
 
@@ -298,5 +310,5 @@ __all__ = [
     "max_preconditioner_size", "min_preconditioning_size", "preconditioner_tolerance", "num_trace_samples",
     "max_root_decomposition_size", "max_lanczos_iterations", "terminate_cg_by_size", "skip_logdet_forward",
     "deterministic_probes", "debug", "memory_efficient", "trace_mode", "verbose_linalg", "fast_computations",
-    "cholesky_jitter", "cholesky_max_tries", "tridiagonal_jitter", "ciq_samples", "cuda_graphs",
+    "cholesky_jitter", "cholesky_max_tries", "tridiagonal_jitter", "ciq_samples", "cuda_graphs", "minres_tolerance", "num_contour_quadrature",
 ]

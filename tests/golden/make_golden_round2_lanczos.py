@@ -58,3 +58,34 @@ for tag, kdt in (("f64", torch.float64), ("f32", torch.float32)):
     np.savez_compressed(os.path.join(OUT, f"kron_added_diag_{tag}.npz"), f0=npy(fs[0]), f1=npy(fs[1]), f2=npy(fs[2]),
                         rhs=npy(rhs), jitter=0.5, solve=npy(sol), inv_quad=npy(iq), logdet=npy(ld), logdet_only=npy(ld_only))
     print("wrote kron_added_diag_" + tag, sol.shape, iq.shape, ld.shape)
+
+# ---- shifted MINRES and contour-integral quadrature (utils/minres.py, utils/contour_integral_quad.py)
+from linear_operator.utils.contour_integral_quad import contour_integral_quad  # noqa: E402
+from linear_operator.utils.minres import minres  # noqa: E402
+
+wm = torch.randn(2, 50, 50, dtype=dt, generator=g)
+am = wm @ wm.mT / 50 + 0.5 * torch.eye(50, dtype=dt)
+bm = torch.randn(2, 50, 3, dtype=dt, generator=g)
+bm[..., 1] = 0.0  # a zero right-hand-side column (masked to zero in the output, minres.py:197)
+sh = torch.tensor([0.0, 0.3, 2.0], dtype=dt)
+minv = 1.0 / am.diagonal(dim1=-1, dim2=-2)
+sol = minres(am.matmul, bm, shifts=sh, max_iter=100)
+sol_pre = minres(am.matmul, bm, shifts=sh, max_iter=100, preconditioner=lambda v: v * minv.unsqueeze(-1))
+sol_neg = minres(am.matmul, bm, shifts=-sh - 0.1, value=-1, max_iter=100)
+sol_vec = minres(am[0].matmul, bm[0, :, 0], max_iter=100)
+np.savez_compressed(os.path.join(OUT, "minres_f64.npz"), A=npy(am), rhs=npy(bm), shifts=npy(sh), minv=npy(minv),
+                    solve=npy(sol), solve_precond=npy(sol_pre), solve_neg=npy(sol_neg), solve_vec=npy(sol_vec))
+print("wrote minres_f64", sol.shape, sol_vec.shape)
+am32, bm32 = am.float(), bm.float()
+sol32 = minres(am32.matmul, bm32, shifts=sh.float(), max_iter=100)
+np.savez_compressed(os.path.join(OUT, "minres_f32.npz"), A=npy(am32), rhs=npy(bm32), shifts=npy(sh.float()), solve=npy(sol32))
+opq = AddedDiagLinearOperator(DenseLinearOperator(am), DiagLinearOperator(torch.full((2, 50), 0.2, dtype=dt)))
+rq = torch.randn(2, 50, 2, dtype=dt, generator=g)
+out = {}
+for inv in (True, False):
+    solves, weights, no_shift, shifts = contour_integral_quad(opq, rq, inverse=inv)
+    tag = "inv" if inv else "sqrt"
+    out.update({f"solves_{tag}": npy(solves), f"weights_{tag}": npy(weights), f"no_shift_{tag}": npy(no_shift),
+                f"shifts_{tag}": npy(shifts), f"result_{tag}": npy((solves * weights).sum(0))})
+np.savez_compressed(os.path.join(OUT, "ciq_f64.npz"), A=npy(am), d=np.full((2, 50), 0.2), rhs=npy(rq), **out)
+print("wrote ciq_f64", {k: v.shape for k, v in out.items()})
