@@ -43,28 +43,24 @@ k_bilinear_dense(int64_t N, int64_t M, int C, const T* __restrict__ Lf, const T*
     const int cw = min(CK, C - c0);
     __syncthreads();
     // rows i0..i0+BM of L are BM runs of cw contiguous elements (one contiguous chunk when cw == C): read them in
-    // element order, scatter c-major; (i, c) advance incrementally -- no division in the loop
+    // element order, scatter c-major.  (i, c) come from the element index by a multiply-shift (exact for e < 2^20 / cw),
+    // so the loads of the unrolled iterations are independent and stay in flight together.
     {
-      const int di = 256 / cw, dc = 256 - di * cw;
-      int i = tid / cw, c = tid - i * cw;
-      for (; i < BM; ) {
+      const uint32_t inv = (1u << 20) / (uint32_t)cw + 1u;
+#pragma unroll 4
+      for (int e = tid; e < BM * cw; e += 256) {
+        const int i = (int)(((uint32_t)e * inv) >> 20), c = e - i * cw;
         T v = (T)0;
         if (i0 + i < N) {
           v = Lb[(i0 + i) * C + c0 + c];
           if (wb) v *= wb[c0 + c];
         }
         Ls[c * LDL + i] = v;
-        i += di;
-        c += dc;
-        if (c >= cw) { c -= cw; ++i; }
       }
-      i = tid / cw;
-      c = tid - i * cw;
-      for (; i < BN; ) {
+#pragma unroll 4
+      for (int e = tid; e < BN * cw; e += 256) {
+        const int i = (int)(((uint32_t)e * inv) >> 20), c = e - i * cw;
         Rs[c * LDR + i] = (j0 + i < M) ? Rb[(j0 + i) * C + c0 + c] : (T)0;
-        i += di;
-        c += dc;
-        if (c >= cw) { c -= cw; ++i; }
       }
     }
     __syncthreads();
