@@ -22,6 +22,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstring>
 
 #include "common.cuh"
 #include "tcgen05_util.cuh"
@@ -32,8 +33,10 @@ constexpr int G3_BM = 128, G3_BN = 128, G3_BK = 32;
 constexpr int G3_THREADS = 512, G3_CONV_THREADS = 256;
 constexpr int G3_TILE_BYTES = 128 * G3_BK * 4;      // 16 KB, either major-ness
 constexpr int G3_STAGE_BYTES = 4 * G3_TILE_BYTES;   // A | B | A_lo | B_lo
-constexpr int G3_STAGES = 3;
-constexpr size_t G3_SMEM = 1024 + (size_t)G3_STAGES * G3_STAGE_BYTES + 256;
+constexpr int G3_MAX_STAGES = 3, G3_MAX_EPI = 6;
+constexpr int G3_EPI_BYTES = 128 * 32 * 4;          // one epilogue chunk: 128 rows x 32 columns, 16 KB
+// operand ring + epilogue chunk ring: 3 x 64 KB + 2 x 16 KB (long contractions) or 2 x 64 KB + 6 x 16 KB (short ones)
+constexpr size_t G3_SMEM = 1024 + 3 * (size_t)G3_STAGE_BYTES + 2 * (size_t)G3_EPI_BYTES + 512;
 
 struct G3Params {
   float* D;
@@ -56,6 +59,9 @@ struct G3Params {
   int64_t kps;           // K range per split (multiple of G3_BK)
   int64_t a_div, b_div;  // operand batch index = batch / div (shared / grouped operands)
   int a_mn, b_mn;
+  int stages, epi_slots; // ring depths (3, 2) or (2, 6)
+  int tma_epi;           // epilogue through shared memory: E chunks TMA-loaded by warp 3, results TMA-stored (needs
+                         // 16-byte aligned D / E rows); 0: direct loads / stores from the epilogue threads
   int d_trans;           // element (m, n) is stored at D[n * ldd + m] (E likewise; the row factors then index n):
                          // lanes = m write consecutive addresses -- the layout to pick when m is the contiguous index
 };
@@ -115,17 +121,22 @@ __device__ __forceinline__ bool g3_decode(const G3Params& p, int64_t it, G3Work&
 }
 
 __global__ void __launch_bounds__(G3_THREADS, 1)
-k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, G3Params p) {
+k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+         const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmE, G3Params p) {
   using namespace ds;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G3_STAGES * G3_STAGE_BYTES);
-  uint64_t* full = bars;                   // TMA -> converters, MMA
-  uint64_t* empty = full + G3_STAGES;      // MMA (commit) -> TMA
-  uint64_t* lo_full = empty + G3_STAGES;   // converters -> MMA
-  uint64_t* acc_full = lo_full + G3_STAGES;  // [2] MMA (commit) -> epilogue
-  uint64_t* acc_empty = acc_full + 2;        // [2] epilogue -> MMA
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int G3_STAGES = p.stages;
+  unsigned char* epi = smem + G3_STAGES * G3_STAGE_BYTES;  // epi_slots x 16 KB, 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + p.epi_slots * G3_EPI_BYTES);
+  uint64_t* full = bars;                       // TMA -> converters, MMA
+  uint64_t* empty = full + G3_MAX_STAGES;      // MMA (commit) -> TMA
+  uint64_t* lo_full = empty + G3_MAX_STAGES;   // converters -> MMA
+  uint64_t* acc_full = lo_full + G3_MAX_STAGES;  // [2] MMA (commit) -> epilogue
+  uint64_t* acc_empty = acc_full + 2;            // [2] epilogue -> MMA
+  uint64_t* e_full = acc_empty + 2;              // [epi_slots] E loader (warp 3) -> epilogue
+  uint64_t* e_empty = e_full + G3_MAX_EPI;       // [epi_slots] epilogue (after its TMA store has read the slot) -> loader
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(e_empty + G3_MAX_EPI);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -140,6 +151,10 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&acc_full[i]), 1);
       mbar_init(smem_u32(&acc_empty[i]), 4);
+    }
+    for (int i = 0; i < p.epi_slots; ++i) {
+      mbar_init(smem_u32(&e_full[i]), 1);
+      mbar_init(smem_u32(&e_empty[i]), 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -223,10 +238,37 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         if (++s == G3_STAGES) { s = 0; ph ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ===================== E loader: feeds the epilogue chunk ring (tma_epi) =====================
+    if (p.tma_epi && elect_one()) {
+      uint64_t pol;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      const bool load_e = p.E != nullptr && p.splits == 1;
+      uint32_t gch = 0;
+      int slot = 0;
+      G3Work wk;
+      for (int64_t wi = 0; g3_decode(p, wi, wk); ++wi) {
+        for (int chunk = 0; chunk < G3_BN / 32; ++chunk) {
+          const int64_t nb = wk.n0 + chunk * 32;
+          if (nb >= p.N) break;
+          mbar_wait(smem_u32(&e_empty[slot]), ((gch / p.epi_slots) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&e_full[slot]);
+          if (load_e) {
+            mbar_arrive_expect_tx(bar, G3_EPI_BYTES);
+            tma_load_3d(smem_u32(epi + slot * G3_EPI_BYTES), &tmE, bar, (int)nb, (int)wk.m0, (int)wk.batch, pol);
+          } else {
+            mbar_arrive(bar);
+          }
+          ++gch;
+          if (++slot == p.epi_slots) slot = 0;
+        }
+      }
+    }
   } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue: thread = output row; overlaps the main loop of the next work item =============
     const int q = warp & 3;
-    uint32_t it = 0;
+    uint32_t it = 0, gch = 0;
+    int eslot = 0;
     G3Work wk;
     for (; g3_decode(p, it, wk); ++it) {
       const uint32_t buf = it & 1;
@@ -268,6 +310,45 @@ k_gemm3x(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+        }
+        if (p.tma_epi) {
+          // results go through the chunk ring: this thread's row of the [128 x 32] chunk (128-byte rows, 16-byte units
+          // XOR-swizzled by row % 8 exactly as TMA laid E down) is combined in place, then each warp TMA-stores its own
+          // 32-row box -- full lines, clipped at the edges of D by the tensor map
+          mbar_wait(smem_u32(&e_full[eslot]), (gch / p.epi_slots) & 1);
+          const int rl = q * 32 + lane;
+          unsigned char* rowp = epi + eslot * G3_EPI_BYTES + rl * 128;
+          const bool use_e = erow != nullptr;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* cell = reinterpret_cast<float4*>(rowp + ((j ^ (rl & 7)) << 4));
+            float4 v = make_float4((__uint_as_float(r[4 * j]) + __uint_as_float(rc[4 * j])) * ra,
+                                   (__uint_as_float(r[4 * j + 1]) + __uint_as_float(rc[4 * j + 1])) * ra,
+                                   (__uint_as_float(r[4 * j + 2]) + __uint_as_float(rc[4 * j + 2])) * ra,
+                                   (__uint_as_float(r[4 * j + 3]) + __uint_as_float(rc[4 * j + 3])) * ra);
+            if (use_e) {
+              const float4 e = *cell;
+              v.x = fmaf(rb, e.x, v.x); v.y = fmaf(rb, e.y, v.y); v.z = fmaf(rb, e.z, v.z); v.w = fmaf(rb, e.w, v.w);
+            }
+            *cell = v;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (wk.m0 + q * 32 < p.M) {
+              const int zb = (p.splits > 1) ? (int)(wk.batch * p.splits + wk.split) : (int)wk.batch;
+              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                           ::"l"(&tmD), "r"(smem_u32(epi + eslot * G3_EPI_BYTES + q * 4096)), "r"((int)nb),
+                             "r"((int)(wk.m0 + q * 32)), "r"(zb)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            mbar_arrive(smem_u32(&e_empty[eslot]));
+          }
+          ++gch;
+          if (++eslot == p.epi_slots) eslot = 0;
+          continue;
         }
         if (!row_ok) continue;
 #pragma unroll
@@ -414,6 +495,27 @@ static bool g3_make_map(CUtensorMap* tm, const float* ptr, int mn, int64_t rows,
   return r == CUDA_SUCCESS;
 }
 
+// row-major (rows x cols) matrices with a batch dimension, boxes of box_rows x 32 columns, SWIZZLE_128B: the epilogue's
+// chunk ring (E loads: 128-row boxes, D stores: one 32-row box per epilogue warp)
+static bool g3_make_rm_map(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int64_t bs,
+                           int64_t nbatch, int box_rows) {
+  PFN_encodeTiled_g3 enc = g3_encode_fn();
+  if (!enc || !ptr) return false;
+  if ((ld % 4) != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return false;
+  if (nbatch > 1 && (bs % 4) != 0) return false;
+  if (rows >= (1LL << 31) || cols >= (1LL << 31) || nbatch >= (1LL << 31)) return false;
+  const int64_t bstride = (nbatch > 1) ? bs : rows * ld;
+  if ((uint64_t)ld * 4 >= (1ULL << 40) || (uint64_t)bstride * 4 >= (1ULL << 40)) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nbatch};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, (cuuint64_t)bstride * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 // Split-K policy.  Two reasons to split: (1) parallelism when there are fewer tiles than SMs; (2) accuracy -- the
 // tensor core adds into its fp32 accumulator with truncation, an error that grows linearly with the number of k steps
 // accumulated in TMEM (measured at K = 10^7: 6e-4 relative with 37 splits, 2e-5 with 1024), so one split never
@@ -510,9 +612,32 @@ extern "C" int lob_gemm3x(int64_t batch, int64_t M, int64_t N, int64_t K, const 
     LOB_REQUIRE(ws && ws_bytes >= need, "lob_gemm3x: workspace too small for the split-K partial sums");
     p.partial = (float*)ws;
   }
+  // epilogue through shared memory + TMA when the output (or the partial-sum buffer) and E are TMA-addressable
+  CUtensorMap tmD, tmE;
+  memset(&tmD, 0, sizeof(tmD));
+  memset(&tmE, 0, sizeof(tmE));
+  p.tma_epi = 0;
+  if (!p.d_trans) {
+    bool ok;
+    if (splits > 1)
+      ok = g3_make_rm_map(&tmD, p.partial, M, N, N, M * N, batch * splits, 32);
+    else
+      ok = (d_dtype == LOB_F32) && g3_make_rm_map(&tmD, p.D, M, N, ldd, d_batch_stride, batch, 32);
+    if (ok && splits == 1 && p.E) ok = g3_make_rm_map(&tmE, p.E, M, N, lde, e_batch_stride, batch, 128);
+    p.tma_epi = ok ? 1 : 0;
+  }
+  // short contractions are epilogue-bound: trade one operand stage for four more chunks in flight
+  const int64_t max_kb = cdiv(std::min<int64_t>(K, p.kps), G3_BK);
+  if (p.tma_epi && max_kb <= 16) {
+    p.stages = 2;
+    p.epi_slots = 6;
+  } else {
+    p.stages = 3;
+    p.epi_slots = 2;
+  }
   LOB_CUDA(cudaFuncSetAttribute(k_gemm3x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G3_SMEM));
   const unsigned grid = (unsigned)std::min<int64_t>(p.sched_flat ? p.total : p.jobs, kNumSMs);
-  k_gemm3x<<<grid, G3_THREADS, G3_SMEM, st>>>(tmA, tmB, p);
+  k_gemm3x<<<grid, G3_THREADS, G3_SMEM, st>>>(tmA, tmB, tmD, tmE, p);
   LOB_TRY(check_launch("k_gemm3x"));
   if (splits > 1) {
     const unsigned rgrid = (unsigned)cdiv(batch * M * N, 256);

@@ -52,7 +52,16 @@ class LowRankRootAddedDiagLinearOperator(AddedDiagLinearOperator):
         if getattr(self, "_gram_cache", None) is None and self._shared_root_constant_diag():
             U = self._shared_root()
             k = U.shape[-1]
-            g0 = _kernels.tn_matmul(U.unsqueeze(0), U.unsqueeze(0), out_dtype=torch.float64).reshape(1, k, k)
+            # U^T U (r x r, contraction over N) in double: on the tensor cores for fp32 roots, with split-K chunks of at
+            # most 1024 rows so that the truncating fp32 accumulate of the tensor core stays below ~5e-6 relative on
+            # the all-positive diagonal sums, partial sums added in double; CUDA cores otherwise
+            g0 = None
+            if U.dtype == torch.float32 and U.shape[0] >= 4096:
+                g0 = _kernels.gemm3x(U.unsqueeze(0), U.unsqueeze(0), trans_a=True, out_dtype=torch.float64,
+                                     splits=min(4096, -(-U.shape[0] // 1024)))
+            if g0 is None:
+                g0 = _kernels.tn_matmul(U.unsqueeze(0), U.unsqueeze(0), out_dtype=torch.float64)
+            g0 = g0.reshape(1, k, k)
             self._gram_cache = (g0 / self._sigma().double().reshape(-1, 1, 1)).reshape(*self.batch_shape, k, k)
         if getattr(self, "_gram_cache", None) is None:
             U = self._linear_op._root_tensor()

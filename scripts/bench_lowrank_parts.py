@@ -47,6 +47,15 @@ alg = 4.0 * (2 * B * N + N * r)
 print(json.dumps({"product": "x = (R - w U^T) / sigma  (B x r)(r x N), fused epilogue", "ms": ms, "GBps": alg / ms / 1e6,
                   "frac_of_hbm_peak": alg / ms / 1e6 / peak, "tflops_fp32_equiv": 2.0 * B * N * r / ms / 1e9,
                   "relerr_vs_fp64": ((x[0, :16].double() - x_ref).norm() / x_ref.norm()).item()}), flush=True)
+G_ref = Ud.mT @ Ud
+for splits in (1024, 4096):
+    G, ms = timed(lambda: _kernels.gemm3x(U.unsqueeze(0), U.unsqueeze(0), trans_a=True, out_dtype=torch.float64, splits=splits))
+    print(json.dumps({"product": "G = U^T U (r x r), split-K, fp64 output", "splits": splits, "ms": ms,
+                      "relerr_vs_fp64": ((G[0] - G_ref).norm() / G_ref.norm()).item(),
+                      "max_rel_diag_err": ((G[0].diagonal() - G_ref.diagonal()).abs() / G_ref.diagonal()).max().item()}), flush=True)
+G2, ms = timed(lambda: _kernels.tn_matmul(U.unsqueeze(0), U.unsqueeze(0), out_dtype=torch.float64))
+print(json.dumps({"product": "G = U^T U on the CUDA cores (k_matmul_tn<float,double>)", "ms": ms,
+                  "relerr_vs_fp64": ((G2[0] - G_ref).norm() / G_ref.norm()).item()}), flush=True)
 del Ud
 w_t, ms_t = timed(lambda: R @ U)
 print(json.dumps({"product": "torch.matmul(R, U) (cuBLAS fp32) for comparison", "ms": ms_t,
