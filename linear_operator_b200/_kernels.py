@@ -775,6 +775,18 @@ def bilinear_dense(left: torch.Tensor, right: torch.Tensor, w: Optional[torch.Te
     Rf = _flat3(right.expand(*batch_shape, M, C))
     B = Lf.shape[0]
     wf = _col_weights(w, batch_shape, C, left)
+    if out is None and left.dtype == torch.float32 and N >= 1024 and M >= 1024 and M % 4 == 0:
+        # tensor cores: G = L diag(w) R^T is a GEMM with K = C.  The 33-column blocks are not TMA-addressable (16-byte
+        # rows), so both factors are copied once into 4-column-aligned buffers (1 % of the gradient's bytes); the
+        # B N^2 result is written by the TMA epilogue of csrc/gemm3x.cu.
+        Cp = -(-C // 4) * 4
+        Lp = torch.zeros(B, N, Cp, dtype=left.dtype, device=left.device)
+        Rp = torch.zeros(B, M, Cp, dtype=left.dtype, device=left.device)
+        Lp[..., :C] = Lf if wf is None else Lf * wf.unsqueeze(-2)
+        Rp[..., :C] = Rf
+        G = gemm3x(Lp, Rp, trans_b=True)
+        if G is not None:
+            return G.reshape(*batch_shape, N, M)
     acc = 1
     if out is None:
         out = torch.empty(B, N, M, dtype=left.dtype, device=left.device)

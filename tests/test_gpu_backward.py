@@ -116,6 +116,19 @@ def test_bilinear_kernels_against_einsum():
         check(npy(_kernels.tri_inverse(C)), npy(torch.linalg.inv(C.double())), tol * 10)
 
 
+def test_bilinear_dense_tensor_core_path_against_einsum():
+    """N, M >= 1024 in fp32: the gradient G = L diag(w) R^T goes through csrc/gemm3x.cu (3xTF32, K = 33 padded to 36);
+    ragged against the 128-wide tiles."""
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    left = torch.randn(2, 1100, 33, device=DEV, generator=gen)
+    right = torch.randn(2, 1028, 33, device=DEV, generator=gen)
+    w = torch.randn(2, 33, device=DEV, generator=gen)
+    want = torch.einsum("bic,bjc,bc->bij", left.double(), right.double(), w.double())
+    check(npy(_kernels.bilinear_dense(left, right, w)), npy(want), 1e-5)
+    want = torch.einsum("bic,bjc->bij", left.double(), right.double())
+    check(npy(_kernels.bilinear_dense(left, right)), npy(want), 1e-5)
+
+
 def test_inv_quad_logdet_backward_mid_size_fp32_vs_oracle():
     """N = 700 (ragged against the 128-wide gradient tiles), batch 2, fp32, rank-12 preconditioner: gradients against
     the oracle's restatement of the reference backward on identical inputs and probes."""
