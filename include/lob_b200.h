@@ -122,6 +122,7 @@ int lob_dense_matmul(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, 
                      int64_t d_stride, double* dots, void* ws, size_t ws_bytes, void* stream);
 
 /* Test hook: pins the fp32 dense-matmul implementation (0 automatic dispatch, 1 dense_stream2, 2 dense_stream,
+ * 5 dense_stream2p (CTA pairs),
  * 3 dense_tc, 4 CUDA cores) so the tests can compare the kernels with each other on the same call.  Every choice
  * computes the same product to fp32 accuracy; nothing in the release library changes numerics through the environment
  * (the harness-only experiment switches of the streaming kernels exist only when compiled with -DLOB_DIAG). */

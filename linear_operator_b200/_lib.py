@@ -194,11 +194,11 @@ def load():
     return lib
 
 
-_DENSE_IMPLS = {None: 0, "auto": 0, "stream2": 1, "stream": 2, "tc": 3, "simt": 4}
+_DENSE_IMPLS = {None: 0, "auto": 0, "stream2": 1, "stream": 2, "tc": 3, "simt": 4, "stream2p": 5}
 
 
 def pin_dense_impl(name=None):
-    """Test hook: pins the fp32 dense-matmul kernel ("stream2", "stream", "tc", "simt"; None = automatic dispatch)."""
+    """Test hook: pins the fp32 dense-matmul kernel ("stream2p", "stream2", "stream", "tc", "simt"; None = automatic dispatch)."""
     check(load().lob_debug_pin_dense_impl(_DENSE_IMPLS[name]), "lob_debug_pin_dense_impl")
 
 

@@ -313,10 +313,16 @@ int dense_matmul_stream2_f32(int64_t B, int64_t M, int64_t K, int64_t C, const f
                              const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
                              cudaStream_t st);
 
-// fp32 dispatch: streaming tcgen05 kernels (need the workspace; dense_stream2.cu for C <= 48, dense_stream.cu up to
-// C = 64) -> first-generation tcgen05 kernel -> CUDA cores.
+size_t dense_stream2p_workspace_bytes(int64_t B, int64_t K, int64_t C);
+int dense_matmul_stream2p_f32(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
+                              const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
+                              const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
+                              cudaStream_t st);
+
+// fp32 dispatch: streaming tcgen05 kernels (need the workspace; the CTA-pair kernel dense_stream2p.cu and
+// dense_stream2.cu for C <= 48, dense_stream.cu up to C = 64) -> first-generation tcgen05 kernel -> CUDA cores.
 // lob_debug_pin_dense_impl() pins one of them (A/B comparisons in the tests; every choice computes the same product).
-static std::atomic<int> g_dense_pin{0};  // 0 auto, 1 stream2, 2 stream, 3 tc, 4 simt
+static std::atomic<int> g_dense_pin{0};  // 0 auto, 1 stream2, 2 stream, 3 tc, 4 simt, 5 stream2p
 static int dense_f32_tensor_paths(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
                                   const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
                                   const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
@@ -327,6 +333,12 @@ static int dense_f32_tensor_paths(int64_t B, int64_t M, int64_t K, int64_t C, co
   // dense_stream2 serves long contractions (streaming regime) and short ones (K <= 256: the preconditioner product
   // Q t with the fused z, <r,z> epilogue -- 1.62 ms at config 2 since its epilogue reduces the fp64 partials with a
   // transpose-reduce, against 2.25 ms for the first-generation kernel); the window in between stays on the older kernel.
+  // long contractions: the CTA-pair kernel (half the X-operand traffic through each SM's shared memory)
+  if (pin == 5 || (!impl && K >= 512)) {
+    int s = dense_matmul_stream2p_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, ws,
+                                      ws_bytes, st);
+    if (s != LOB_ERR_UNSUPPORTED) return s;
+  }
   const bool pinned_stream2 = pin == 1;
   if (pinned_stream2 || (!impl && (K >= 512 || (K <= 256 && a_bs != 0)))) {
     int s = dense_matmul_stream2_f32(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots, ws,
@@ -344,7 +356,7 @@ static int dense_f32_tensor_paths(int64_t B, int64_t M, int64_t K, int64_t C, co
 }
 
 extern "C" int lob_debug_pin_dense_impl(int32_t impl) {
-  LOB_REQUIRE(impl >= 0 && impl <= 4, "lob_debug_pin_dense_impl: 0 auto, 1 stream2, 2 stream, 3 tc, 4 simt");
+  LOB_REQUIRE(impl >= 0 && impl <= 5, "lob_debug_pin_dense_impl: 0 auto, 1 stream2, 2 stream, 3 tc, 4 simt, 5 stream2p");
   lob::g_dense_pin.store(impl);
   return LOB_OK;
 }
@@ -353,7 +365,8 @@ extern "C" size_t lob_dense_matmul_workspace_bytes(int32_t dtype, int64_t B, int
   (void)M;
   if (dtype != LOB_F32) return 0;
   const size_t w1 = lob::dense_stream_workspace_bytes(B, K, C), w2 = lob::dense_stream2_workspace_bytes(B, K, C);
-  return w1 > w2 ? w1 : w2;
+  const size_t w3 = lob::dense_stream2p_workspace_bytes(B, K, C);
+  return std::max(w1, std::max(w2, w3));
 }
 
 extern "C" int lob_dense_matmul_ex(int32_t dtype, int64_t B, int64_t M, int64_t K, int64_t C, const void* A,

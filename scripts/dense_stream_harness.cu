@@ -2,7 +2,8 @@
 // shapes / configurations, a check of how the tensor core converts fp32 -> tf32, bit-for-bit repeatability under load,
 // and a throughput sweep at the BASELINE config-2 tile shape.  Build:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Iinclude -Ilinear_operator_b200/csrc \
-//        scripts/dense_stream_harness.cu linear_operator_b200/csrc/dense_stream.cu linear_operator_b200/csrc/api.cu \
+//        scripts/dense_stream_harness.cu linear_operator_b200/csrc/dense_stream.cu \
+//        linear_operator_b200/csrc/dense_stream2.cu linear_operator_b200/csrc/dense_stream2p.cu linear_operator_b200/csrc/api.cu \
 //        -o scripts/dense_stream_harness
 #include <cuda_runtime.h>
 #include <math.h>
@@ -33,15 +34,30 @@ int dense_matmul_stream2_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, con
                                  const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
                                  const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
                                  cudaStream_t st, D2Config cfg);
+struct P2Config {
+  int acc_bufs, bk, sa, grid, dbg;
+};
+size_t dense_stream2p_workspace_bytes(int64_t B, int64_t K, int64_t C);
+int dense_matmul_stream2p_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs,
+                                  const float* X, float* Y, const float* E, const float* alpha, int64_t alpha_bs,
+                                  const float* d, int64_t d_bs, int64_t d_st, double* dots, void* ws, size_t ws_bytes,
+                                  cudaStream_t st, P2Config cfg);
 }  // namespace lob
 
-static int g_impl = 1;  // 1: dense_stream.cu, 2: dense_stream2.cu
+static int g_impl = 1;  // 1: dense_stream.cu, 2: dense_stream2.cu, 4: dense_stream2p.cu (CTA pairs)
+static inline bool gen2() { return g_impl == 2 || g_impl == 4; }
 static size_t ws_bytes_for(int64_t B, int64_t K, int64_t C) {
+  if (g_impl == 4) return lob::dense_stream2p_workspace_bytes(B, K, C);
   return g_impl == 2 ? lob::dense_stream2_workspace_bytes(B, K, C) : lob::dense_stream_workspace_bytes(B, K, C);
 }
 static int launch(int64_t B, int64_t M, int64_t K, int64_t C, const float* A, int64_t lda, int64_t a_bs, const float* X,
                   float* Y, const float* E, const float* alpha, int64_t alpha_bs, const float* d, int64_t d_bs,
                   int64_t d_st, double* dots, void* ws, size_t wsb, lob::DsConfig cfg) {
+  if (g_impl == 4) {
+    lob::P2Config c4{(cfg.dbg & 1024) ? 1 : 2, cfg.bk, cfg.sa, cfg.grid, cfg.dbg & ~1024};
+    return lob::dense_matmul_stream2p_f32_cfg(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots,
+                                              ws, wsb, 0, c4);
+  }
   if (g_impl == 2) {
     lob::D2Config c2{(cfg.dbg & 1024) ? 1 : 2, cfg.bk, cfg.sa, cfg.grid, cfg.dbg, cfg.lo_mode};  // lo_mode slot carries xmode for generation 2
     return lob::dense_matmul_stream2_f32_cfg(B, M, K, C, A, lda, a_bs, X, Y, E, alpha, alpha_bs, d, d_bs, d_st, dots,
@@ -269,7 +285,7 @@ int main(int argc, char** argv) {
     Case cs{1, 256, K, 16, false, false, false, false};
     double de;
     int st;
-    lob::DsConfig cfg{g_impl == 3 ? 0 : 16, 0, 0, g_impl == 2 ? 1 : 0, 0, 0};
+    lob::DsConfig cfg{g_impl == 3 ? 0 : (g_impl == 4 ? 32 : 16), 0, 0, g_impl == 2 ? 1 : 0, 0, 0};
     const double err = run_case(cs, cfg, 64, &de, &st);
     printf("[bias] all-positive data K=%lld: normalised err %.3e\n", (long long)K, err);
     g_positive = false;
@@ -286,14 +302,14 @@ int main(int argc, char** argv) {
   for (int bk : {16, 32}) {
     for (int lo : {0, 1}) {
       for (const Case& cs : cases) {
-        if (lo == 1 && g_impl != 2 && !(cs.M == 700 && g_impl == 1)) continue;  // other conversion model: one shape
+        if (lo == 1 && !gen2() && !(cs.M == 700 && g_impl == 1)) continue;  // other conversion model: one shape
         if (g_impl >= 2 && cs.C > 48) continue;
         if (g_impl == 3 && bk == 16) continue;
         double de;
         int st;
-        lob::DsConfig cfg{g_impl == 3 ? 0 : bk, 0, 0, (g_impl == 2) ? 0 : lo, 0, (g_impl == 2 && lo == 1) ? 1024 : 0};
+        lob::DsConfig cfg{g_impl == 3 ? 0 : bk, 0, 0, gen2() ? 0 : lo, 0, (gen2() && lo == 1) ? 1024 : 0};
         const double err = run_case(cs, cfg, 40, &de, &st);
-        const bool ok = (lo == 1 && g_impl != 2) || (err < 2e-6 && de < 1e-12);
+        const bool ok = (lo == 1 && !gen2()) || (err < 2e-6 && de < 1e-12);
         if (!ok) ++failures;
         printf("[case] BK=%d lo=%d B=%lld M=%lld K=%lld C=%lld diag=%d dots=%d ex=%d : err %.3e dots_err %.3e %s\n", bk,
                lo, (long long)cs.B, (long long)cs.M, (long long)cs.K, (long long)cs.C, cs.diag, cs.dots, cs.ex, err, de,
@@ -331,9 +347,13 @@ int main(int argc, char** argv) {
     // generation 3: {sa (bk slot unused -> 0), sa, sx, grid, dbg}
     const V variants3[] = {{0, 0, 0, 0, 0}, {0, 4, 0, 0, 0}, {0, 3, 0, 0, 0}, {0, 5, 3, 0, 0}, {0, 0, 0, 0, 1},
                            {0, 0, 0, 0, 2}, {0, 0, 0, 0, 4}, {0, 0, 0, 0, 6}, {0, 0, 0, 0, 128}};
+    // CTA pairs: {bk, sa, -, grid, dbg}; dbg 1024 = single-buffered accumulators (more operand slots)
+    const V variants4[] = {{32, 0, 0, 0, 0}, {32, 0, 0, 0, 1024}, {32, 4, 0, 0, 0}, {16, 0, 0, 0, 2048}, {32, 0, 0, 0, 0},
+                           {32, 0, 0, 0, 1}, {32, 0, 0, 0, 2}, {32, 0, 0, 0, 4}};
     std::vector<V> variants;
     if (g_impl == 3) variants.assign(variants3, variants3 + sizeof(variants3) / sizeof(V));
     else if (g_impl == 2) variants.assign(variants2, variants2 + sizeof(variants2) / sizeof(V));
+    else if (g_impl == 4) variants.assign(variants4, variants4 + sizeof(variants4) / sizeof(V));
     else variants.assign(variants1, variants1 + sizeof(variants1) / sizeof(V));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));

@@ -1,5 +1,6 @@
-"""The tcgen05 split-TF32 dense operator matmuls (csrc/dense_stream2.cu: persistent A-stationary streaming kernel, the
-default; csrc/dense_stream.cu: its X-stationary predecessor, serves 48 < C <= 64; csrc/dense_tc.cu: first-generation
+"""The tcgen05 split-TF32 dense operator matmuls (csrc/dense_stream2p.cu: CTA-pair version of the A-stationary streaming
+kernel, the default for long contractions; csrc/dense_stream2.cu: its single-CTA form, serves short contractions and
+calls without a workspace; csrc/dense_stream.cu: its X-stationary predecessor, serves 48 < C <= 64; csrc/dense_tc.cu: first-generation
 kernel, kept as the workspace-free fallback and for short contractions) against an fp64 product of the same fp32
 inputs and against the CUDA-core kernel.  fp32 inputs; the bar is fp32 accuracy (error << 1e-4, north-star parity
 tolerance)."""
@@ -15,7 +16,7 @@ from linear_operator_b200 import _kernels, _lib  # noqa: E402
 DEV = "cuda:0"
 
 
-@pytest.fixture(params=["stream2", "stream", "tc"])
+@pytest.fixture(params=["stream2p", "stream2", "stream", "tc"])
 def impl(request):
     """Pins the fp32 tensor-core kernel through the library's explicit test hook (lob_debug_pin_dense_impl)."""
     _lib.pin_dense_impl(request.param)
@@ -129,10 +130,11 @@ def test_dense_matmul_generalised_epilogue(dtype, constant_diag, impl):
     assert ((T2.double() - ref2).abs().max() / ref2.abs().max()).item() < tol
 
 
-def test_dense_stream_accumulation_bias_on_positive_data():
+@pytest.mark.parametrize("kernel", ["stream2p", "stream2"])
+def test_dense_stream_accumulation_bias_on_positive_data(kernel):
     """Worst case for the tensor core's truncating fp32 accumulate: all-positive operands, no cancellation.  The bias is
     linear in K (measured 1.5e-8 * K relative); this pins it below the 1e-4 parity bar at N = 5000 and documents it."""
-    _lib.pin_dense_impl("stream2")
+    _lib.pin_dense_impl(kernel)
     try:
         g = torch.Generator(device=DEV).manual_seed(11)
         A = torch.rand(1, 512, 5000, device=DEV, generator=g)
