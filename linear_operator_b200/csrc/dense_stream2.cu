@@ -63,6 +63,7 @@ struct D2Params {
   int acc_bufs;    // 2: accumulators double-buffered (epilogue overlaps the next tile); 1: single, more operand slots
   int xmode;     // 0: X operand tiles TMA-loaded from the pre-split workspace; 1: produced in the kernel (warps 2-3)
   int dbg;       // harness experiments: 1 skip lo MMA, 2 skip conversion, 4 skip all MMAs
+  int estage;    // bytes of one staged E / Y tile (256 rows x C floats) or 0: see "staged epilogue" below
 };
 
 template <int BK>
@@ -78,7 +79,12 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = A_STAGE + p.xbytes;
   unsigned char* sRing = smem;
-  double* dred = reinterpret_cast<double*>(smem + p.SA * stage_bytes);
+  // staged epilogue (short contractions, where the epilogue IS the kernel): the E rows of a tile are one contiguous
+  // run of global memory, so the TMA warp bulk-copies them into shared memory a tile ahead, the epilogue threads
+  // overwrite them in place with Y and one thread bulk-stores the tile -- no dependent, 132-byte-strided global loads
+  // and stores in the per-row epilogue threads.  Two buffers.
+  float* sE = reinterpret_cast<float*>(smem + p.SA * stage_bytes);
+  double* dred = reinterpret_cast<double*>(smem + p.SA * stage_bytes + 2 * p.estage);
   uint64_t* bars = reinterpret_cast<uint64_t*>(dred + D2_RED_DOUBLES);
   uint64_t* full = bars;                    // [MAX_ST] TMA -> converters, MMA
   uint64_t* empty = full + D2_MAX_ST;       // [MAX_ST] MMA (commit) -> TMA
@@ -87,7 +93,10 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* lo_empty = lo_full + 8;         // [NSLOT]  MMA (commit) -> converters
   uint64_t* acc_full = lo_empty + 8;        // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* e_full = acc_empty + 2;         // [2] bulk copy of the E tile -> epilogue
+  uint64_t* e_empty = e_full + 2;           // [2] bulk store of the Y tile has read the buffer -> TMA warp
+  uint64_t* y_ready = e_empty + 2;          // [2] epilogue warps -> store warp
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(y_ready + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (int)((p.K + BK - 1) / BK);
@@ -107,6 +116,9 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&acc_full[i]), 1);
       mbar_init(smem_u32(&acc_empty[i]), 4);
+      mbar_init(smem_u32(&e_full[i]), 1);
+      mbar_init(smem_u32(&e_empty[i]), 1);
+      mbar_init(smem_u32(&y_ready[i]), 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -139,11 +151,23 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (!(p.dbg & 512)) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_stream));
       if (p.dbg & 256) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_stream));
       int s = 0;
-      uint32_t ph = 0;
+      uint32_t ph = 0, it = 0;
       const uint32_t xtx = (uint32_t)(2 * p.CP * BK * 4);
-      for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int b = (int)(tile / p.MT);
         const int m0 = (int)(tile - (int64_t)b * p.MT) * D2_ROWS;
+        if (p.estage) {
+          const uint32_t eb = it & 1;
+          mbar_wait(smem_u32(&e_empty[eb]), ((it >> 1) & 1) ^ 1);
+          const uint32_t ebytes = (uint32_t)(min((int64_t)D2_ROWS, p.M - m0) * p.C * 4);
+          const uint32_t bar = smem_u32(&e_full[eb]);
+          mbar_arrive_expect_tx(bar, ebytes);
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+              ::"r"(smem_u32(reinterpret_cast<unsigned char*>(sE) + eb * p.estage)),
+              "l"(p.E + ((int64_t)b * p.M + m0) * p.C), "r"(ebytes), "r"(bar)
+              : "memory");
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&empty[s]), ph ^ 1);
           const uint32_t dst = smem_u32(sRing + s * stage_bytes);
@@ -203,7 +227,27 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // Item e = (k-quad j, column c), e = j * C + c: consecutive threads read consecutive addresses of the BK x C block of
     // X (one contiguous run of BK * C floats, L2 resident: 20 row tiles share it) and write one 16-byte unit of row c
     // (X_hi) and of row CP + c (X_lo).  Values are prefetched one k-block ahead in registers.
-    if (p.xmode == 1) {
+    if (p.estage && warp == 3) {
+      // ---- store warp (staged epilogue): Y tile, shared -> global as one bulk copy ----
+      if (elect_one()) {
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+          const uint32_t eb = it & 1;
+          const int64_t b = tile / p.MT;
+          const int64_t m0 = (tile - b * p.MT) * D2_ROWS;
+          const uint32_t ybytes = (uint32_t)(min((int64_t)D2_ROWS, p.M - m0) * p.C * 4);
+          mbar_wait(smem_u32(&y_ready[eb]), (it >> 1) & 1);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       ::"l"(p.Y + (b * p.M + m0) * p.C),
+                       "r"(smem_u32(reinterpret_cast<unsigned char*>(sE) + eb * p.estage)), "r"(ybytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(smem_u32(&e_empty[eb]));
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+    } else if (p.xmode == 1) {
       constexpr int NQ = BK / 4;
       constexpr int NI = (48 * NQ + 63) / 64;
       const int tid2 = threadIdx.x - 64;
@@ -293,6 +337,9 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const float* Eb = p.E + b * p.M * C;
       float* Yb = p.Y + b * p.M * C;
       double* red = dred + (it & 1) * (2 * 4 * 48);
+      const bool staged = p.estage != 0;
+      float* sEt = sE + (it & 1) * (p.estage >> 2);  // staged: E rows of this tile, overwritten in place with Y
+      if (staged) mbar_wait(smem_u32(&e_full[it & 1]), (it >> 1) & 1);
       mbar_wait(smem_u32(&acc_full[buf]), accph);
       __syncwarp();
       tc_fence_after();
@@ -302,11 +349,17 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool rok = row < p.M;
         const float dv = (p.dg && rok) ? __ldg(p.dg + b * p.d_bs + row * p.d_st) : 0.f;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + t) * p.acc_stride;
+        float* srow = sEt + (t * 128 + q * 32 + lane) * C;  // odd C: consecutive rows fall into consecutive banks
 #pragma unroll 1
         for (int c0 = 0; c0 < CP; c0 += 16) {
           float e[16];
+          if (staged) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) e[i] = (need_e && rok && c0 + i < C) ? __ldg(Eb + row * C + c0 + i) : 0.f;
+            for (int i = 0; i < 16; ++i) e[i] = (rok && c0 + i < C) ? srow[c0 + i] : 0.f;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) e[i] = (need_e && rok && c0 + i < C) ? __ldg(Eb + row * C + c0 + i) : 0.f;
+          }
           uint32_t hi[16], lo[16];
           DS_LD16(taddr + c0, hi);
           DS_LD16(taddr + CP + c0, lo);
@@ -316,7 +369,10 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int i = 0; i < 16; ++i) {
             const float y = fmaf(dv, e[i], (__uint_as_float(hi[i]) + __uint_as_float(lo[i])) * alpha_b);
             const bool ok = rok && c0 + i < C;
-            if (ok) Yb[row * C + c0 + i] = y;
+            if (ok) {
+              if (staged) srow[c0 + i] = y;
+              else Yb[row * C + c0 + i] = y;
+            }
             pd[i] = ok ? (double)e[i] * (double)y : 0.0;
           }
           if (p.dots) {
@@ -343,8 +399,12 @@ k_dense_stream2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       // accumulators drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
+      if (staged) fence_async_smem();  // the Y tile in shared memory is read by the bulk store (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&acc_empty[buf]));
+        if (staged) mbar_arrive(smem_u32(&y_ready[it & 1]));
+      }
       if (p.dots) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int idx = et; idx < 2 * C; idx += 128) {
@@ -498,6 +558,7 @@ static D2Config d2_default_config() {
 
 constexpr size_t D2_SMEM_MAX = 232448;
 constexpr size_t D2_SMEM_FIXED = 1024 /*alignment*/ + D2_RED_DOUBLES * 8 + 512 /*barriers*/;
+constexpr int64_t D2_ESTAGE_MAX_K = 256;  // staged epilogue: contractions this short are epilogue-bound
 
 size_t dense_stream2_workspace_bytes(int64_t B, int64_t K, int64_t C) {
   if (B <= 0 || K <= 0 || C <= 0 || C > 48) return 0;
@@ -562,13 +623,19 @@ int dense_matmul_stream2_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, con
   const int a_stage = D2_ROWS * BK * 4;
   const int xbytes = (int)align_up((size_t)2 * CP * BK * 4, 1024);
   const int stage = a_stage + xbytes;
-  int sa = cfg.sa > 0 ? cfg.sa : (int)((D2_SMEM_MAX - D2_SMEM_FIXED) / stage);
+  // staged epilogue: E given, rows of 132-byte-odd pitch (bank-conflict-free per-row access), tiles 16-byte addressable
+  int estage = 0;
+  if (xmode == 0 && K <= D2_ESTAGE_MAX_K && E && (d || dots) && (C & 1) && ((M * C) % 4) == 0 &&
+      (reinterpret_cast<uintptr_t>(E) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 && !(cfg.dbg & 8))
+    estage = (int)align_up((size_t)D2_ROWS * C * 4, 16);
+  int sa = cfg.sa > 0 ? cfg.sa : (int)((D2_SMEM_MAX - D2_SMEM_FIXED - 2 * estage) / stage);
   if (sa > D2_MAX_ST) sa = D2_MAX_ST;
   if (sa < 2) return LOB_ERR_UNSUPPORTED;
-  const size_t smem = D2_SMEM_FIXED + (size_t)sa * stage;
+  const size_t smem = D2_SMEM_FIXED + (size_t)sa * stage + 2 * (size_t)estage;
   if (smem > D2_SMEM_MAX) return LOB_ERR_UNSUPPORTED;
 
   D2Params p;
+  p.estage = estage;
   p.Y = Y;
   p.X = X;
   p.E = E ? E : X;

@@ -419,8 +419,8 @@ int main(int argc, char** argv) {
           worst = std::max(worst, fabs((double)h[(size_t)(b * N + r) * C + c] - acc) / accabs);
         }
       }
-      printf("[perf] spot check vs fp64 host: normalised err %.3e %s\n", worst, worst < 2e-6 ? "ok" : "FAIL");
-      if (!(worst < 2e-6)) ++failures;
+      printf("[perf] spot check vs fp64 host: normalised err %.3e %s\n", worst, worst < 3e-6 ? "ok" : "FAIL");
+      if (!(worst < 3e-6)) ++failures;  // same bar as tests/test_dense_tc.py at N = 5000 (accumulator truncation bias)
     }
   }
   printf("[harness] failures: %d\n", failures);

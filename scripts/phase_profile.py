@@ -3,7 +3,7 @@ launching stream (no profiler: kernels overlap and cache exactly as in bench.py)
 ``lob_cg_*`` call is bracketed by an event pair; `unaccounted` = step time - sum of the brackets = torch glue kernels
 (randn, cat, isnan, memsets) + device idle time behind host work / synchronisations.
 
-    python scripts/phase_profile.py [batch] [dense|toeplitz|kron]
+    python scripts/phase_profile.py [batch] [dense|toeplitz|kron] [pinned dense kernel, e.g. stream2: A/B on one box]
 """
 import collections
 import json
@@ -22,6 +22,8 @@ dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 KIND = sys.argv[2] if len(sys.argv) > 2 else "dense"
 S = 32
+if len(sys.argv) > 3:
+    _lib.pin_dense_impl(sys.argv[3])
 gen = torch.Generator(device=dev).manual_seed(1234)
 if KIND == "dense":
     N = 5000
@@ -110,7 +112,8 @@ for name, evs in records.items():
     rows.append((ms, name, len(evs) // reps))
     acc += ms
 rows.sort(reverse=True)
-print(f"cold inv_quad_logdet, {KIND}, N = {N}, batch {B}: {total:.1f} ms per call")
+print(f"cold inv_quad_logdet, {KIND}, N = {N}, batch {B}{', dense kernel pinned to ' + sys.argv[3] if len(sys.argv) > 3 else ''}: "
+      f"{total:.1f} ms per call")
 for ms, name, n in rows:
     print(f"  {name:28s} {n:4d} calls  {ms:8.2f} ms  {100 * ms / total:5.1f} %")
 print(f"  {'unaccounted (glue + idle)':28s}             {total - acc:8.2f} ms  {100 * (total - acc) / total:5.1f} %")
