@@ -427,7 +427,7 @@ def run_ours(args):
     # DRAM traffic of the dominant kernel from the committed ncu capture (per batch element, scaled to this batch)
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_dense_stream2_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_dense_stream2p_traffic.json")))
         if int(tr["n"]) == N and int(tr["columns"]) == C:
             traffic = float(tr["dram_bytes_per_batch_element"]) * B
     except Exception:
@@ -436,11 +436,11 @@ def run_ours(args):
     if mm_ms:
         avg_ms = sum(mm_ms) / len(mm_ms)
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "dense operator matmul Y = A X + d.X with fused <p,Ap> partials (k_split_x2 + k_dense_stream2)",
+        roof = {"bound": "hbm", "kernel": "dense operator matmul Y = A X + d.X with fused <p,Ap> partials (k_split_x2p + k_dense_stream2p, CTA pairs)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write of k_dense_stream2 at batch 256, scaled "
-                "per batch element (profiles/r2_dense_stream2_traffic.json)" if traffic else None,
+                "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write of k_dense_stream2p at batch 256, scaled "
+                "per batch element (profiles/r2_dense_stream2p_traffic.json)" if traffic else None,
                 "avg_launch_ms": avg_ms, "launches_timed": len(mm_ms),
                 "share_of_step": sum(mm_ms) / elapsed_ms if world == 1 else None,
                 "algorithmic_bytes_per_launch": alg_bytes}
