@@ -408,6 +408,12 @@ class AddedDiagPreconditioner:
                                    ptr(logdet_r), ptr(info), ptr(ws), stream(L)),
             "lob_precond_factor",
         )
+        # fp32 ranks that are not a multiple of 4 (the reference's default is 15): Q gets zero columns up to the next
+        # multiple of 4 (at least 8), so that its rows are 16-byte addressable and both products of the apply take
+        # the TMA / cp.async kernels instead of the generic CUDA-core ones; zero columns change no product.
+        kp = max(8, -(-k // 4) * 4) if dty == torch.float32 else k
+        if kp != k:
+            rinv = torch.cat([rinv, rinv.new_zeros(B, k, kp - k)], dim=-1)
         Q = gemm3x(Ls.reshape(B, N, k), rinv) if dty == torch.float32 and N >= 2048 else None  # Q1 = L R^-1
         if Q is None:
             Q = matmul_nn(Ls.reshape(B, N, k), rinv)

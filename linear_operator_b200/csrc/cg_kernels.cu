@@ -7,6 +7,10 @@
 // (double) to (B, nchunks, C); every consumer CTA re-adds the nchunks partials in a fixed order.  No atomics on the
 // data path, no host synchronisation: the stop test / tridiagonal bookkeeping of the reference runs in a one-CTA
 // control kernel that sets device-side control words, and every kernel early-exits once `stop` is set.
+#include <math.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace lob {
@@ -18,7 +22,7 @@ struct CgLayout {
   int cx, ry;
   // byte offsets into the workspace
   size_t off_status, off_rhs_norm, off_rhs_zero, off_conv, off_alpha, off_beta, off_rz, off_resid, off_prev_ar,
-      off_prev_beta, off_parts_a, off_parts_rr, off_parts_rz, total;
+      off_prev_beta, off_parts_a, off_parts_rr, off_parts_rz, off_fold, total;
 };
 
 static CgLayout cg_layout(const lob_cg_params* p) {
@@ -29,12 +33,25 @@ static CgLayout cg_layout(const lob_cg_params* p) {
   L.cx = (int)(p->C < 128 ? p->C : 128);
   L.ry = 256 / L.cx;
   if (L.ry < 1) L.ry = 1;
-  int64_t target = (int64_t)kNumSMs * 8;
-  int64_t nch = cdiv(target, p->B);
+  // Row chunks per batch element: the vector kernels keep 5 CTAs per SM resident (registers), so the grid B * nch is
+  // chosen to fill whole waves of 5 * 148 CTAs (a 1.7-wave grid ran its second wave 70 % full; small batches with the
+  // former cap of 64 chunks left a third of the slots empty).  Consumers re-add the nch partials per column in a fixed
+  // order, so nch stays <= 256.
+  const int64_t slots = (int64_t)kNumSMs * 5;
   int64_t maxch = cdiv(p->N, (int64_t)L.ry * 4);
-  if (nch > maxch) nch = maxch;
-  if (nch > 64) nch = 64;
-  if (nch < 1) nch = 1;
+  if (maxch > 256) maxch = 256;
+  int64_t nch = 1;
+  double best_eff = -1.0;
+  for (int64_t c = std::max<int64_t>(1, cdiv(2 * slots, p->B)); c <= maxch; ++c) {
+    const double waves = (double)(p->B * c) / (double)slots;
+    const double eff = waves / ceil(waves);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      nch = c;
+    }
+    if (eff >= 0.97 || c >= 8 * cdiv(2 * slots, p->B)) break;
+  }
+  if (best_eff < 0) nch = maxch;  // fewer rows than two waves' worth: as many chunks as the rows allow
   L.rows_per_chunk = cdiv(p->N, nch);
   L.nchunks = (int)cdiv(p->N, L.rows_per_chunk);
   const size_t bc = (size_t)p->B * p->C;
@@ -58,6 +75,7 @@ static CgLayout cg_layout(const lob_cg_params* p) {
   L.off_parts_a = take(bc * L.nchunks * 8);
   L.off_parts_rr = take(bc * L.nchunks * 8);
   L.off_parts_rz = take(bc * L.nchunks * 8);
+  L.off_fold = take(2 * bc * 8);
   L.total = o;
   return L;
 }
@@ -76,6 +94,7 @@ struct CgPtrs {
   double* parts_a;
   double* parts_rr;
   double* parts_rz;
+  double* fold;  // [2][B*C]: caller-supplied partial sums folded to one value per column (k_fold_parts)
 };
 
 static CgPtrs cg_ptrs(const CgLayout& L, void* ws) {
@@ -94,6 +113,7 @@ static CgPtrs cg_ptrs(const CgLayout& L, void* ws) {
   P.parts_a = (double*)(b + L.off_parts_a);
   P.parts_rr = (double*)(b + L.off_parts_rr);
   P.parts_rz = (double*)(b + L.off_parts_rz);
+  P.fold = (double*)(b + L.off_fold);
   return P;
 }
 
@@ -131,6 +151,25 @@ __device__ __forceinline__ double sum_parts(const double* parts, int64_t b, int 
   const int tx = threadIdx.x, ty = threadIdx.y, RY = blockDim.y, CX = blockDim.x; \
   const int64_t base = b * d.N * d.C;                                            \
   (void)red; (void)row0; (void)row1; (void)tx; (void)ty; (void)RY; (void)CX; (void)base;
+
+// ---- out[b,c] = sum_i parts[b,i,c]: folds long lists of caller-supplied partials (the fused epilogues of the matmul
+// kernels emit one per 128 operator rows: 7813 at N = 10^6) once, instead of in the prologue of every consumer CTA ----
+constexpr int kFoldThreshold = 64;
+__global__ void k_fold_parts(const double* __restrict__ parts, int n_parts, int C, double* __restrict__ out,
+                             const lob_cg_status* status) {
+  if (status && status->stop) return;
+  extern __shared__ double red[];
+  const int64_t b = blockIdx.x;
+  const int tx = threadIdx.x, ty = threadIdx.y, RY = blockDim.y, CX = blockDim.x;
+  for (int c0 = 0; c0 < C; c0 += CX) {
+    const int c = c0 + tx;
+    double acc = 0.0;
+    if (c < C)
+      for (int i = ty; i < n_parts; i += RY) acc += parts[(b * n_parts + i) * C + c];
+    const double s = reduce_over_ty(acc, red);
+    if (ty == 0 && c < C) out[b * C + c] = s;
+  }
+}
 
 // ---- generic: parts[b,chunk,c] = sum_rows u*v -------------------------------------------------------------
 template <typename T>
@@ -471,6 +510,18 @@ static Launch make_launch(const CgLayout& L) {
   return l;
 }
 
+// long caller-supplied partial lists are folded once into ws (slot 0: <p,Ap>, slot 1: <r,z>)
+static int fold_parts(const CgLayout& L, const CgPtrs& P, const Launch& l, const double*& parts, int& n_parts, int slot,
+                      const lob_cg_status* status, cudaStream_t st) {
+  if (!parts || n_parts <= kFoldThreshold) return LOB_OK;
+  double* out = P.fold + (size_t)slot * L.B * L.C;
+  k_fold_parts<<<(unsigned)L.B, l.block, l.smem, st>>>(parts, n_parts, (int)L.C, out, status);
+  LOB_TRY(check_launch("k_fold_parts"));
+  parts = out;
+  n_parts = 1;
+  return LOB_OK;
+}
+
 }  // namespace lob
 
 using namespace lob;
@@ -541,6 +592,7 @@ extern "C" int lob_cg_direction_init(const lob_cg_params* p, void* ws, const voi
       if (rz_partials) {
         parts = rz_partials;
         n_rz = n_rz_parts;
+        LOB_TRY(fold_parts(L, P, l, parts, n_rz, 1, nullptr, st));
       } else {
         k_dots_partials<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, (const scalar_t*)z, (const scalar_t*)r,
                                                                    P.parts_rz, nullptr);
@@ -567,6 +619,7 @@ extern "C" int lob_cg_step_xr(const lob_cg_params* p, void* ws, int32_t k, const
   LOB_DISPATCH_DTYPE(p->dtype, {
     const double* parts = pap_partials;
     int nparts = n_parts;
+    LOB_TRY(fold_parts(L, P, l, parts, nparts, 0, P.status, st));
     if (!parts) {
       k_dots_partials<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, (const scalar_t*)pvec, (const scalar_t*)ap,
                                                                  P.parts_a, P.status);
@@ -602,6 +655,7 @@ extern "C" int lob_cg_step_p(const lob_cg_params* p, void* ws, int32_t k, const 
       if (rz_partials) {  // <r,z> came out of the preconditioner's fused epilogue
         parts_rz = rz_partials;
         n_rz = n_rz_parts;
+        LOB_TRY(fold_parts(L, P, l, parts_rz, n_rz, 1, P.status, st));
       } else {
         k_dots_partials<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, (const scalar_t*)z, (const scalar_t*)r,
                                                                    P.parts_rz, P.status);
