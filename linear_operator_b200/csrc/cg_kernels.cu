@@ -15,6 +15,9 @@
 
 namespace lob {
 
+constexpr int kFoldThreshold = 64;  // caller-supplied partial lists longer than this are folded first
+constexpr int kFoldParts = 16;      // ... to this many partials per column (one CTA each)
+
 struct CgLayout {
   int64_t B, N, C;
   int nchunks;
@@ -75,7 +78,7 @@ static CgLayout cg_layout(const lob_cg_params* p) {
   L.off_parts_a = take(bc * L.nchunks * 8);
   L.off_parts_rr = take(bc * L.nchunks * 8);
   L.off_parts_rz = take(bc * L.nchunks * 8);
-  L.off_fold = take(2 * bc * 8);
+  L.off_fold = take(2 * bc * kFoldParts * 8);
   L.total = o;
   return L;
 }
@@ -154,20 +157,22 @@ __device__ __forceinline__ double sum_parts(const double* parts, int64_t b, int 
 
 // ---- out[b,c] = sum_i parts[b,i,c]: folds long lists of caller-supplied partials (the fused epilogues of the matmul
 // kernels emit one per 128 operator rows: 7813 at N = 10^6) once, instead of in the prologue of every consumer CTA ----
-constexpr int kFoldThreshold = 64;
 __global__ void k_fold_parts(const double* __restrict__ parts, int n_parts, int C, double* __restrict__ out,
                              const lob_cg_status* status) {
   if (status && status->stop) return;
   extern __shared__ double red[];
-  const int64_t b = blockIdx.x;
+  const int64_t b = blockIdx.y;
+  const int slice = blockIdx.x;  // of kFoldParts
+  const int per = (n_parts + kFoldParts - 1) / kFoldParts;
+  const int i0 = slice * per, i1 = min(n_parts, i0 + per);
   const int tx = threadIdx.x, ty = threadIdx.y, RY = blockDim.y, CX = blockDim.x;
   for (int c0 = 0; c0 < C; c0 += CX) {
     const int c = c0 + tx;
     double acc = 0.0;
     if (c < C)
-      for (int i = ty; i < n_parts; i += RY) acc += parts[(b * n_parts + i) * C + c];
+      for (int i = i0 + ty; i < i1; i += RY) acc += parts[(b * n_parts + i) * C + c];
     const double s = reduce_over_ty(acc, red);
-    if (ty == 0 && c < C) out[b * C + c] = s;
+    if (ty == 0 && c < C) out[(b * kFoldParts + slice) * C + c] = s;
   }
 }
 
@@ -514,11 +519,11 @@ static Launch make_launch(const CgLayout& L) {
 static int fold_parts(const CgLayout& L, const CgPtrs& P, const Launch& l, const double*& parts, int& n_parts, int slot,
                       const lob_cg_status* status, cudaStream_t st) {
   if (!parts || n_parts <= kFoldThreshold) return LOB_OK;
-  double* out = P.fold + (size_t)slot * L.B * L.C;
-  k_fold_parts<<<(unsigned)L.B, l.block, l.smem, st>>>(parts, n_parts, (int)L.C, out, status);
+  double* out = P.fold + (size_t)slot * L.B * L.C * kFoldParts;
+  k_fold_parts<<<dim3(kFoldParts, (unsigned)L.B), l.block, l.smem, st>>>(parts, n_parts, (int)L.C, out, status);
   LOB_TRY(check_launch("k_fold_parts"));
   parts = out;
-  n_parts = 1;
+  n_parts = kFoldParts;
   return LOB_OK;
 }
 

@@ -12,6 +12,9 @@
 //     the split) into a double-buffered shared-memory tile of 32 rows;
 //   * per row and thread: 3 LDS.128 (two 4-wide chunks of the P row -- chunk t and chunk t + half, so consecutive
 //     threads read consecutive 16-byte words -- and one chunk of the Q row) for 32 FFMA;
+//   * narrow P (few 8 x 4 output tiles, e.g. 18 for the reference's default rank 15 padded to 16): G row groups of
+//     threads share the tiles -- group g takes rows g, g + G, ... of every shared-memory tile -- and are added in a
+//     fixed order at the end, so a CTA still has >= 4 busy warps;
 //   * per-split partial sums are combined in double by k_reduce_splits (matmul_simt.cu): deterministic.
 #include "common.cuh"
 
@@ -31,7 +34,7 @@ __device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, uint32
 // LDP = 8 * half (padded I), LDQ = 4 * nj (padded J); blockDim.x = round_up(half * nj, 32)
 __global__ void __launch_bounds__(256)
 k_tn_skinny(int64_t N, int I, int J, const float* __restrict__ P, int64_t p_bs, const float* __restrict__ Q,
-            int64_t q_bs, float* __restrict__ partial, int nsplit, int64_t rows_per_split, int half, int nj) {
+            int64_t q_bs, float* __restrict__ partial, int nsplit, int64_t rows_per_split, int half, int nj, int G) {
   extern __shared__ __align__(16) float tns_smem[];
   const int LDP = 8 * half, LDQ = 4 * nj;
   float* Ps = tns_smem;                       // [2][TK][LDP]
@@ -69,8 +72,10 @@ k_tn_skinny(int64_t N, int I, int J, const float* __restrict__ P, int64_t p_bs, 
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  const int ti = tid % half, tj = tid / half;
-  const bool active = tj < nj;
+  const int ntile_out = half * nj;            // 8 x 4 output tiles
+  const int tt = tid % ntile_out, g = tid / ntile_out;
+  const int ti = tt % half, tj = tt / half;
+  const bool active = g < G;
   float acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -92,7 +97,7 @@ k_tn_skinny(int64_t N, int I, int J, const float* __restrict__ P, int64_t p_bs, 
       const float* prow = Ps + stage * TNS_TK * LDP + ti * 4;
       const float* qrow = Qs + stage * TNS_TK * LDQ + tj * 4;
 #pragma unroll 8
-      for (int kk = 0; kk < TNS_TK; ++kk) {
+      for (int kk = g; kk < TNS_TK; kk += G) {
         const float4 a0 = *reinterpret_cast<const float4*>(prow + kk * LDP);
         const float4 a1 = *reinterpret_cast<const float4*>(prow + kk * LDP + half * 4);
         const float4 q4 = *reinterpret_cast<const float4*>(qrow + kk * LDQ);
@@ -107,7 +112,25 @@ k_tn_skinny(int64_t N, int I, int J, const float* __restrict__ P, int64_t p_bs, 
     __syncthreads();
   }
 
-  if (active) {
+  // row groups: g = G - 1 hands its sums to g = G - 2, ... down to g = 0 (fixed order), through the free tile buffers
+  for (int gg = G - 1; gg >= 1; --gg) {
+    float* xch = tns_smem + tt * 32;
+    if (active && g == gg) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xch[i * 4 + j] = acc[i][j];
+    }
+    __syncthreads();
+    if (active && g == gg - 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += xch[i * 4 + j];
+    }
+    __syncthreads();
+  }
+  if (active && g == 0) {
     float* out = partial + ((b * nsplit + split) * I) * J;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -133,7 +156,7 @@ int tn_skinny_nsplit(int64_t B, int64_t N) {
   int64_t ns = cdiv(5 * slots, B);
   const int64_t maxs = std::max<int64_t>(1, N / 128);
   if (ns > maxs) ns = maxs;
-  if (ns > 64) ns = 64;
+  if (ns > 512) ns = 512;  // small batches of long vectors need the CTAs for bytes in flight (64 left the GPU 3/4 idle)
   if (ns < 1) ns = 1;
   const int64_t rps = cdiv(N, ns);
   return (int)cdiv(N, rps);
@@ -144,7 +167,10 @@ int launch_tn_skinny_f32(int64_t B, int64_t N, int64_t I, int64_t J, const float
   const int pchunks = (int)((I + 3) / 4);
   const int half = (pchunks + 1) / 2;
   const int nj = (int)((J + 3) / 4);
-  const int nthr = (int)align_up((size_t)half * nj, 32);
+  const int tiles = half * nj;
+  int G = 1;  // row groups (a power of two: divides the 32-row tile)
+  while (tiles < 64 && G < 8 && tiles * G * 2 <= 256) G *= 2;
+  const int nthr = (int)align_up((size_t)tiles * G, 32);
   if (nthr > 256) return LOB_ERR_UNSUPPORTED;
   const int64_t rows_per_split = cdiv(N, nsplit);
   const size_t smem = (size_t)2 * TNS_TK * (8 * half + 4 * nj) * sizeof(float);
@@ -157,7 +183,7 @@ int launch_tn_skinny_f32(int64_t B, int64_t N, int64_t I, int64_t J, const float
     attr_set = true;
   }
   dim3 grid((unsigned)nsplit, (unsigned)B);
-  k_tn_skinny<<<grid, nthr, smem, st>>>(N, (int)I, (int)J, P, p_bs, Q, q_bs, partial, nsplit, rows_per_split, half, nj);
+  k_tn_skinny<<<grid, nthr, smem, st>>>(N, (int)I, (int)J, P, p_bs, Q, q_bs, partial, nsplit, rows_per_split, half, nj, G);
   return check_launch("k_tn_skinny");
 }
 

@@ -16,7 +16,7 @@ DEV = "cuda:0"
 @pytest.mark.parametrize(
     "B,N,I,J",
     [(3, 5000, 100, 33), (2, 1000, 8, 1), (2, 777, 128, 48), (1, 300, 52, 17), (2, 4096, 100, 32), (5, 260, 12, 5),
-     (2, 1000, 130, 33), (2, 1000, 50, 33), (1, 200, 100, 33)],
+     (2, 1000, 130, 33), (2, 1000, 50, 33), (1, 200, 100, 33), (2, 100003, 16, 33), (3, 3001, 24, 11), (1, 999, 32, 48)],
 )
 def test_tn_matmul_matches_fp64(B, N, I, J):
     g = torch.Generator(device=DEV).manual_seed(B * 1000 + N + I + J)
