@@ -251,6 +251,19 @@ int lob_toeplitz_mul(int32_t dtype, int64_t B, int64_t C, int64_t H, const void*
                      void* stream);
 int lob_toeplitz_unpad(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* yt, double scale,
                        const void* X, const void* d, int64_t d_batch_stride, int64_t d_stride, void* Y, void* stream);
+/* The same product through complex FFTs of column PAIRS (the symmetric embedding has a real spectrum, so two real
+ * columns ride one C2C transform: no real-to-complex pre/post-processing passes, transposes folded into pack/unpack).
+ * colmax: maxbits (B, C) = bit patterns of max_n |X| (uint32 / uint64);  pack: zt (B, ceil(C/2), L) complex =
+ * transposed column pairs, each column scaled by an exact power of two to [1, 2), zero above N;  mulr: zt *= fr
+ * (fr (B|1, L/2+1) real spectrum, indexed min(k, L-k));  unpack: Y (B,N,C) = scale / s_c * zt[..., :N] (+ d (.) X). */
+int lob_toeplitz_colmax(int32_t dtype, int64_t B, int64_t N, int64_t C, const void* X, void* maxbits, void* stream);
+int lob_toeplitz_pack(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* X, const void* maxbits,
+                      void* zt, void* stream);
+int lob_toeplitz_mulr(int32_t dtype, int64_t B, int64_t P, int64_t L, const void* fr, int64_t fr_batch_stride, void* zt,
+                      void* stream);
+int lob_toeplitz_unpack(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* zt, double scale,
+                        const void* maxbits, const void* X, const void* d, int64_t d_batch_stride, int64_t d_stride,
+                        void* Y, void* stream);
 
 /* generic batched small-K product  Y (B, M, C) = A (B|1, M, K) X (B, K, C): Q t, L eps, U w
  * (added_diag_linear_operator.py:137, _linear_operator.py:2784-2791, low_rank_root_added_diag_...py:83).

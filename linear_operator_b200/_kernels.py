@@ -685,31 +685,39 @@ def toeplitz_matmul(col: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor
         fc_bs = fc.shape[-1]
     Y = torch.empty(B, N, C, dtype=X.dtype, device=X.device)
     dd, d_bs, d_st = _diag_args(d, batch_shape, N)
-    # The padded transposes and the spectrum are 3 x (B, C, L) scratch: at BASELINE config 4 (B = 64, N = 2^20, 33
-    # columns) that is 53 GB per product on top of the solver state.  Batch elements are independent, so the product is
-    # done in batch chunks whose scratch stays below ~4.5 GB each (16 elements at config 4).
-    chunk = max(1, min(B, int(TOEPLITZ_SCRATCH_BYTES // (C * L * X.element_size()))))
+    # The embedding of a symmetric Toeplitz matrix has a real spectrum: column PAIRS ride one complex transform
+    # (csrc/structured.cu, "complex FFTs of column pairs").  Scratch: two (B, ceil(C/2), L) complex arrays (transform
+    # input and output) -- 2 x 17.8 GB at BASELINE config 4 (B = 64, N = 2^20, 33 columns) -- so the product runs in
+    # batch chunks whose arrays stay below ~4.5 GB each (16 elements at config 4); batch elements are independent.
+    fr = fc.real.contiguous()  # (B | 1, L / 2 + 1)
+    fr_bs = 0 if fc_bs == 0 else fr.shape[-1]
+    P = (C + 1) // 2
+    cdtype = torch.complex64 if X.dtype == torch.float32 else torch.complex128
+    bits_dtype = torch.int32 if X.dtype == torch.float32 else torch.int64
+    chunk = max(1, min(B, int(TOEPLITZ_SCRATCH_BYTES // (2 * P * L * X.element_size()))))
     for b0 in range(0, B, chunk):
         b1 = min(B, b0 + chunk)
         nb = b1 - b0
-        xt = torch.empty(nb, C, L, dtype=X.dtype, device=X.device)
-        check(lib.lob_toeplitz_pad(dt(X), nb, N, C, L, ptr(Xf[b0:b1]), ptr(xt), stream(X)), "lob_toeplitz_pad")
-        fx = torch.fft.rfft(xt)  # cuFFT R2C, batched over (B, C)
-        del xt
-        H = fx.shape[-1]
-        fc_c = fc if fc_bs == 0 else fc[b0:b1]
-        check(lib.lob_toeplitz_mul(dt(X), nb, C, H, ptr(fc_c), fc_bs, ptr(fx), stream(X)), "lob_toeplitz_mul")
-        # cuFFT C2R, un-normalised (norm="forward" puts the 1/L on the forward transform, which we did not ask for):
-        # the 1/L goes into the un-padding kernel instead of a separate full pass over (B, C, L)
-        yt = torch.fft.irfft(fx, n=L, norm="forward")
-        del fx
+        xs = Xf[b0:b1]
+        maxbits = torch.empty(nb, C, dtype=bits_dtype, device=X.device)
+        check(lib.lob_toeplitz_colmax(dt(X), nb, N, C, ptr(xs), ptr(maxbits), stream(X)), "lob_toeplitz_colmax")
+        zt = torch.empty(nb, P, L, dtype=cdtype, device=X.device)
+        check(lib.lob_toeplitz_pack(dt(X), nb, N, C, L, ptr(xs), ptr(maxbits), ptr(zt), stream(X)), "lob_toeplitz_pack")
+        # cuFFT C2C, batched over (B, P); out-of-place on purpose: with out= torch transforms into a temporary and
+        # then copies (a full extra pass, measured)
+        zt = torch.fft.fft(zt, dim=-1)
+        fr_c = fr if fr_bs == 0 else fr[b0:b1]
+        check(lib.lob_toeplitz_mulr(dt(X), nb, P, L, ptr(fr_c), fr_bs, ptr(zt), stream(X)), "lob_toeplitz_mulr")
+        # un-normalised inverse (norm="forward" puts the 1/L on the forward transform, which we did not ask for): the
+        # 1/L goes into the unpack kernel instead of a separate full pass
+        zt = torch.fft.ifft(zt, dim=-1, norm="forward")
         dd_c = dd if (dd is None or d_bs == 0) else dd[b0:b1]
         check(
-            lib.lob_toeplitz_unpad(dt(X), nb, N, C, L, ptr(yt), 1.0 / L, ptr(Xf[b0:b1]), ptr(dd_c), d_bs, d_st,
-                                   ptr(Y[b0:b1]), stream(X)),
-            "lob_toeplitz_unpad",
+            lib.lob_toeplitz_unpack(dt(X), nb, N, C, L, ptr(zt), 1.0 / L, ptr(maxbits), ptr(xs), ptr(dd_c), d_bs, d_st,
+                                    ptr(Y[b0:b1]), stream(X)),
+            "lob_toeplitz_unpack",
         )
-        del yt
+        del zt
     return Y.reshape(*batch_shape, N, C)
 
 

@@ -140,6 +140,13 @@ _SIGS = {
     "lob_toeplitz_pad": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, c_int64, _P, _P, _P]),
     "lob_toeplitz_embed": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, c_int64, _P, _P]),
     "lob_toeplitz_mul": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, c_int64, _P, _P]),
+    "lob_toeplitz_colmax": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, _P, _P]),
+    "lob_toeplitz_pack": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P]),
+    "lob_toeplitz_mulr": (ctypes.c_int, [c_int32, c_int64, c_int64, c_int64, _P, c_int64, _P, _P]),
+    "lob_toeplitz_unpack": (
+        ctypes.c_int,
+        [c_int32, c_int64, c_int64, c_int64, c_int64, _P, c_double, _P, _P, _P, c_int64, c_int64, _P, _P],
+    ),
     "lob_toeplitz_unpad": (
         ctypes.c_int,
         [c_int32, c_int64, c_int64, c_int64, c_int64, _P, c_double, _P, _P, c_int64, c_int64, _P, _P],

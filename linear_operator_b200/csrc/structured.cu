@@ -133,6 +133,173 @@ k_toeplitz_unpad(int64_t N, int64_t C, int64_t L, const T* __restrict__ yt, T sc
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Symmetric Toeplitz product through COMPLEX FFTs of column pairs (utils/toeplitz.py:131-149).  The circulant embedding
+// of a symmetric Toeplitz matrix has a REAL spectrum, so  ifft(F . fft(x_a + i x_b)) = y_a + i y_b : two real columns
+// ride one complex transform, with none of the real-to-complex pre/post-processing passes and no separate transposes:
+//   colmax (per-column max |x|) -> pack (transpose + pair + zero-pad, columns scaled by an exact power of two to a
+//   common magnitude so the rounding of one column cannot leak into a much smaller partner) -> cuFFT C2C (in place) ->
+//   mulr (real spectrum) -> cuFFT C2C inverse (in place) -> unpack (first N samples, 1/L, un-scale, + d (.) X).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct PairOf;
+template <> struct PairOf<float> { using type = float2; using bits = unsigned int; };
+template <> struct PairOf<double> { using type = double2; using bits = unsigned long long; };
+__device__ __forceinline__ unsigned int abs_bits(float v) { return __float_as_uint(fabsf(v)); }
+__device__ __forceinline__ unsigned long long abs_bits(double v) { return (unsigned long long)__double_as_longlong(fabs(v)); }
+// exact power-of-two scale that brings a column with max |x| = m to [1, 2); 1 for an all-zero (or non-finite) column
+__device__ __forceinline__ float col_scale(unsigned int mb) {
+  const int e = (int)(mb >> 23);
+  if (e == 0 || e >= 254) return 1.f;
+  return __uint_as_float((unsigned int)(254 - e) << 23);
+}
+__device__ __forceinline__ double col_scale(unsigned long long mb) {
+  const int e = (int)(mb >> 52);
+  if (e == 0 || e >= 2046) return 1.0;
+  return __longlong_as_double((long long)(2046 - e) << 52);
+}
+
+constexpr int TP_ROWS = 64;  // vector rows per CTA in pack / unpack
+
+// maxbits[b, c] = bit pattern of max_n |X[b, n, c]|  (non-negative IEEE values order like unsigned integers; the
+// result of an atomic max does not depend on the order of arrival).  block (cx = min(C, 128), ry), grid (chunks, B)
+template <typename T>
+__global__ void k_toeplitz_colmax(int64_t N, int64_t C, int64_t rows_per_cta, const T* __restrict__ X,
+                                  typename PairOf<T>::bits* __restrict__ maxbits) {
+  using bits_t = typename PairOf<T>::bits;
+  extern __shared__ unsigned long long cm_red[];  // [ry][cx]
+  const int64_t b = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+  const int tx = threadIdx.x, ty = threadIdx.y, CX = blockDim.x, RY = blockDim.y;
+  for (int64_t c0 = 0; c0 < C; c0 += CX) {
+    const int64_t c = c0 + tx;
+    bits_t m = 0;
+    if (c < C) {
+      const T* col = X + b * N * C + c;
+      int64_t r = r0 + ty;
+      for (; r + 3 * RY < r1; r += 4 * RY) {
+        const T v0 = col[r * C], v1 = col[(r + RY) * C], v2 = col[(r + 2 * RY) * C], v3 = col[(r + 3 * RY) * C];
+        m = max(max(m, abs_bits(v0)), max(abs_bits(v1), max(abs_bits(v2), abs_bits(v3))));
+      }
+      for (; r < r1; r += RY) m = max(m, abs_bits(col[r * C]));
+    }
+    cm_red[ty * CX + tx] = m;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+      unsigned long long mm = 0;
+      for (int i = 0; i < RY; ++i) mm = max(mm, cm_red[i * CX + tx]);
+      if (mm) atomicMax(maxbits + b * C + c, (bits_t)mm);
+    }
+    __syncthreads();
+  }
+}
+
+// zt (B, P, L) complex, P = ceil(C / 2):  zt[b, p, l] = (s_2p X[b, l, 2p], s_2p+1 X[b, l, 2p+1]) for l < N, 0 above
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_toeplitz_pack(int64_t N, int64_t C, int64_t L, const T* __restrict__ X,
+                const typename PairOf<T>::bits* __restrict__ maxbits, typename PairOf<T>::type* __restrict__ zt) {
+  using T2 = typename PairOf<T>::type;
+  extern __shared__ __align__(16) unsigned char tp_smem[];
+  T* tile = reinterpret_cast<T*>(tp_smem);  // [TP_ROWS][C | 1]
+  const int ld = (int)C | 1;
+  T* sc = tile + TP_ROWS * ld;              // [C]
+  const int64_t b = blockIdx.y, n0 = (int64_t)blockIdx.x * TP_ROWS;
+  const int P = (int)((C + 1) / 2);
+  const int tid = threadIdx.x;
+  T2* zb = zt + b * P * L;
+  if (n0 >= N) {  // zero padding
+    for (int idx = tid; idx < P * TP_ROWS; idx += 256) {
+      const int pp = idx / TP_ROWS, l = idx - pp * TP_ROWS;
+      if (n0 + l < L) zb[(int64_t)pp * L + n0 + l] = T2{(T)0, (T)0};
+    }
+    return;
+  }
+  for (int c = tid; c < C; c += 256) sc[c] = col_scale(maxbits[b * C + c]);
+  const int rows = (int)min((int64_t)TP_ROWS, N - n0);
+  const T* src = X + (b * N + n0) * C;
+  {  // the rows of this block are one contiguous run: flat coalesced loads, (row, column) advanced without divisions
+    const int dq = 256 / (int)C, dr = 256 - dq * (int)C;
+    int r = tid / (int)C, c = tid - r * (int)C;
+    for (int e = tid; e < rows * (int)C; e += 256) {
+      tile[r * ld + c] = src[e];
+      r += dq;
+      c += dr;
+      if (c >= (int)C) { c -= (int)C; ++r; }
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < P * TP_ROWS; idx += 256) {
+    const int pp = idx / TP_ROWS, l = idx - pp * TP_ROWS;
+    if (n0 + l >= L) continue;
+    T2 z{(T)0, (T)0};
+    if (l < rows) {
+      z.x = tile[l * ld + 2 * pp] * sc[2 * pp];
+      if (2 * pp + 1 < C) z.y = tile[l * ld + 2 * pp + 1] * sc[2 * pp + 1];
+    }
+    zb[(int64_t)pp * L + n0 + l] = z;
+  }
+}
+
+// zt[b, p, k] *= fr[b, min(k, L - k)]   (fr: real spectrum of the embedding, L / 2 + 1 entries; two samples per thread)
+template <typename T>
+__global__ void k_toeplitz_mulr(int64_t P, int64_t L, const T* __restrict__ fr, int64_t fr_bs,
+                                typename PairOf<T>::type* __restrict__ zt, int64_t total_pairs) {
+  using T2 = typename PairOf<T>::type;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_pairs) return;
+  const int64_t e = 2 * idx;  // L is even: a pair of samples never straddles two sequences
+  const int64_t seq = e / L, k = e - seq * L;
+  const int64_t b = seq / P;
+  const T* f = fr + b * fr_bs;
+  const T f0 = f[k <= L - k ? k : L - k];
+  const T f1 = f[k + 1 <= L - k - 1 ? k + 1 : L - k - 1];
+  T2 a = zt[e], c = zt[e + 1];
+  a.x *= f0, a.y *= f0, c.x *= f1, c.y *= f1;
+  zt[e] = a;
+  zt[e + 1] = c;
+}
+
+// Y[b, n, c] = (scale / s_c) * part_c(zt[b, c / 2, n]) (+ d (.) X)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_toeplitz_unpack(int64_t N, int64_t C, int64_t L, const typename PairOf<T>::type* __restrict__ zt, T scale,
+                  const typename PairOf<T>::bits* __restrict__ maxbits, const T* __restrict__ X,
+                  const T* __restrict__ d, int64_t d_bs, int64_t d_st, T* __restrict__ Y) {
+  using T2 = typename PairOf<T>::type;
+  extern __shared__ __align__(16) unsigned char tp_smem[];
+  T* tile = reinterpret_cast<T*>(tp_smem);
+  const int ld = (int)C | 1;
+  T* sc = tile + TP_ROWS * ld;
+  const int64_t b = blockIdx.y, n0 = (int64_t)blockIdx.x * TP_ROWS;
+  const int P = (int)((C + 1) / 2);
+  const int tid = threadIdx.x;
+  const int rows = (int)min((int64_t)TP_ROWS, N - n0);
+  // an all-zero input column gives exactly zero (not its partner's rounding noise)
+  for (int c = tid; c < C; c += 256) sc[c] = maxbits[b * C + c] ? scale / col_scale(maxbits[b * C + c]) : (T)0;
+  const T2* zb = zt + b * P * L;
+  for (int idx = tid; idx < P * TP_ROWS; idx += 256) {
+    const int pp = idx / TP_ROWS, l = idx - pp * TP_ROWS;
+    if (l < rows) {
+      const T2 z = zb[(int64_t)pp * L + n0 + l];
+      tile[l * ld + 2 * pp] = z.x;
+      if (2 * pp + 1 < C) tile[l * ld + 2 * pp + 1] = z.y;
+    }
+  }
+  __syncthreads();
+  const int64_t base = (b * N + n0) * C;
+  const int dq = 256 / (int)C, dr = 256 - dq * (int)C;
+  int r = tid / (int)C, c = tid - r * (int)C;
+  for (int e = tid; e < rows * (int)C; e += 256) {
+    T v = tile[r * ld + c] * sc[c];
+    if (d) v += d[b * d_bs + (n0 + r) * d_st] * X[base + e];
+    Y[base + e] = v;
+    r += dq;
+    c += dr;
+    if (c >= (int)C) { c -= (int)C; ++r; }
+  }
+}
+
 // cap = I + G; W <- cap^-1 W via Cholesky in a double workspace held in global memory (L2 resident), one CTA per
 // batch element.  logdet_cap = 2 sum log diag chol(cap).
 template <typename T>
@@ -266,6 +433,73 @@ extern "C" int lob_toeplitz_mul(int32_t dtype, int64_t B, int64_t C, int64_t H, 
     return fail(LOB_ERR_ARG, "dtype must be LOB_F32 or LOB_F64");
   }
   return check_launch("k_toeplitz_mul");
+}
+
+extern "C" int lob_toeplitz_colmax(int32_t dtype, int64_t B, int64_t N, int64_t C, const void* X, void* maxbits,
+                                   void* stream) {
+  LOB_REQUIRE(B > 0 && N > 0 && C > 0, "lob_toeplitz_colmax: sizes must be positive");
+  LOB_REQUIRE(B <= 65535, "lob_toeplitz_colmax: flattened batch > 65535 not supported");
+  LOB_REQUIRE(X && maxbits, "lob_toeplitz_colmax: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  LOB_CUDA(cudaMemsetAsync(maxbits, 0, (size_t)B * C * dsize(dtype), st));
+  const int cx = (int)(C < 128 ? C : 128), ry = 256 / cx > 0 ? 256 / cx : 1;
+  int64_t chunks = cdiv((int64_t)kNumSMs * 8, B);
+  const int64_t maxch = cdiv(N, (int64_t)ry * 4);
+  if (chunks > maxch) chunks = maxch;
+  const int64_t rows = cdiv(N, chunks);
+  dim3 grid((unsigned)cdiv(N, rows), (unsigned)B);
+  const size_t smem = sizeof(unsigned long long) * cx * ry;
+  LOB_DISPATCH_DTYPE(dtype, {
+    k_toeplitz_colmax<scalar_t><<<grid, dim3(cx, ry), smem, st>>>(N, C, rows, (const scalar_t*)X,
+                                                                   (typename PairOf<scalar_t>::bits*)maxbits);
+    return check_launch("k_toeplitz_colmax");
+  });
+}
+
+extern "C" int lob_toeplitz_pack(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* X,
+                                 const void* maxbits, void* zt, void* stream) {
+  LOB_REQUIRE(B > 0 && N > 0 && C > 0 && L >= N, "lob_toeplitz_pack: bad sizes");
+  LOB_REQUIRE(B <= 65535 && C <= 4096, "lob_toeplitz_pack: flattened batch > 65535 or more than 4096 columns not supported");
+  LOB_REQUIRE(X && maxbits && zt, "lob_toeplitz_pack: NULL pointer");
+  dim3 grid((unsigned)cdiv(L, TP_ROWS), (unsigned)B);
+  LOB_DISPATCH_DTYPE(dtype, {
+    const size_t smem = sizeof(scalar_t) * ((size_t)TP_ROWS * ((int)C | 1) + C);
+    LOB_REQUIRE(smem <= 48 * 1024, "lob_toeplitz_pack: too many columns for one shared-memory tile");
+    k_toeplitz_pack<scalar_t><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        N, C, L, (const scalar_t*)X, (const typename PairOf<scalar_t>::bits*)maxbits,
+        (typename PairOf<scalar_t>::type*)zt);
+    return check_launch("k_toeplitz_pack");
+  });
+}
+
+extern "C" int lob_toeplitz_mulr(int32_t dtype, int64_t B, int64_t P, int64_t L, const void* fr, int64_t fr_batch_stride,
+                                 void* zt, void* stream) {
+  LOB_REQUIRE(B > 0 && P > 0 && L > 0 && (L % 2) == 0, "lob_toeplitz_mulr: sizes must be positive, L even");
+  LOB_REQUIRE(fr && zt, "lob_toeplitz_mulr: NULL pointer");
+  const int64_t total = B * P * (L / 2);
+  LOB_DISPATCH_DTYPE(dtype, {
+    k_toeplitz_mulr<scalar_t><<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        P, L, (const scalar_t*)fr, fr_batch_stride, (typename PairOf<scalar_t>::type*)zt, total);
+    return check_launch("k_toeplitz_mulr");
+  });
+}
+
+extern "C" int lob_toeplitz_unpack(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* zt,
+                                   double scale, const void* maxbits, const void* X, const void* d,
+                                   int64_t d_batch_stride, int64_t d_stride, void* Y, void* stream) {
+  LOB_REQUIRE(B > 0 && N > 0 && C > 0 && L >= N, "lob_toeplitz_unpack: bad sizes");
+  LOB_REQUIRE(B <= 65535 && C <= 4096, "lob_toeplitz_unpack: flattened batch > 65535 or more than 4096 columns not supported");
+  LOB_REQUIRE(zt && maxbits && Y && (!d || X), "lob_toeplitz_unpack: NULL pointer");
+  dim3 grid((unsigned)cdiv(N, TP_ROWS), (unsigned)B);
+  LOB_DISPATCH_DTYPE(dtype, {
+    const size_t smem = sizeof(scalar_t) * ((size_t)TP_ROWS * ((int)C | 1) + C);
+    LOB_REQUIRE(smem <= 48 * 1024, "lob_toeplitz_unpack: too many columns for one shared-memory tile");
+    k_toeplitz_unpack<scalar_t><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        N, C, L, (const typename PairOf<scalar_t>::type*)zt, (scalar_t)scale,
+        (const typename PairOf<scalar_t>::bits*)maxbits, (const scalar_t*)X, (const scalar_t*)d, d_batch_stride,
+        d_stride, (scalar_t*)Y);
+    return check_launch("k_toeplitz_unpack");
+  });
 }
 
 extern "C" int lob_toeplitz_unpad(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* yt,

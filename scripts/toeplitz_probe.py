@@ -1,0 +1,19 @@
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+from linear_operator_b200 import _kernels
+dev = "cuda:0"
+B, N, C = 16, 2**20, 33
+j = torch.arange(N, device=dev, dtype=torch.float32)
+col = torch.exp(-0.5 * (j[None, :] / 50.0) ** 2).repeat(B, 1)
+X = torch.randn(B, N, C, device=dev)
+d = torch.full((B, N), 0.5, device=dev)
+fc = _kernels.toeplitz_embed_fft(col)
+for _ in range(3):
+    Y = _kernels.toeplitz_matmul(col, X, d, fc_cache=fc)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    Y = _kernels.toeplitz_matmul(col, X, d, fc_cache=fc)
+e1.record(); torch.cuda.synchronize()
+print("toeplitz_matmul ms", e0.elapsed_time(e1) / 5)

@@ -232,6 +232,26 @@ def test_toeplitz_subbatch_column_broadcast():
     check(npy(y), want, 1e-12)
 
 
+def test_toeplitz_matmul_column_pairs_of_very_different_scale():
+    """toeplitz_matmul packs two real columns into one complex FFT; each column is scaled by an exact power of two
+    first, so a column 10^12 times smaller than its partner keeps its own relative accuracy (per-column check against
+    the fp64 oracle), also with an odd column count, an even one and a single column."""
+    gen = torch.Generator(device=DEV).manual_seed(17)
+    N = 1500
+    col = torch.exp(-0.5 * (torch.arange(N, device=DEV) / 7.0) ** 2)
+    for C in (5, 4, 1):
+        scales = torch.tensor([1e6, 1e-6, 1.0, 1e-3, 1e3][:C], device=DEV)
+        X = torch.randn(N, C, device=DEV, generator=gen) * scales
+        if C == 5:
+            X[:, 2] = 0.0  # an all-zero column beside a non-zero partner
+        y = ToeplitzLinearOperator(col)._matmul(X)
+        want = ko.sym_toeplitz_matmul(npy(col).astype(np.float64), npy(X).astype(np.float64))
+        for c in range(C):
+            ref = np.abs(want[:, c]).max()
+            err = np.abs(npy(y)[:, c] - want[:, c]).max()
+            assert err <= 2e-5 * ref, f"column {c} (scale {scales[c].item():g}): {err / max(ref, 1e-300):.2e}"  # zero column: exactly 0
+
+
 def test_cfg4_toeplitz_baseline_shape_vs_oracle():
     """BASELINE configs[3]: toeplitz_matmul at N = 2^20 with the full 33-column block, one batch element, fp32, against
     the oracle's length-(2N-1) complex-FFT restatement (utils/toeplitz.py:131-149)."""
