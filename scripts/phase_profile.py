@@ -92,7 +92,8 @@ def step():
     return op.inv_quad_logdet(rhs, logdet=True)
 
 
-with settings.num_trace_samples(S), settings.max_preconditioner_size(100):
+RANK = int(os.environ.get("PRECOND_RANK", "100"))  # BASELINE config 2 names rank 100; 15 is the reference's default
+with settings.num_trace_samples(S), settings.max_preconditioner_size(RANK):
     for _ in range(2):
         step()
     torch.cuda.synchronize()
@@ -112,7 +113,7 @@ for name, evs in records.items():
     rows.append((ms, name, len(evs) // reps))
     acc += ms
 rows.sort(reverse=True)
-print(f"cold inv_quad_logdet, {KIND}, N = {N}, batch {B}{', dense kernel pinned to ' + sys.argv[3] if len(sys.argv) > 3 else ''}: "
+print(f"cold inv_quad_logdet, {KIND}, N = {N}, batch {B}, preconditioner rank {RANK}{', dense kernel pinned to ' + sys.argv[3] if len(sys.argv) > 3 else ''}: "
       f"{total:.1f} ms per call")
 for ms, name, n in rows:
     print(f"  {name:28s} {n:4d} calls  {ms:8.2f} ms  {100 * ms / total:5.1f} %")
