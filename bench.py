@@ -301,6 +301,31 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, index):
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers of the e2e leg are
+    allocated (first touch places them on that node).  Round 1's 4- and 8-GPU e2e runs uploaded at half the per-GPU PCIe
+    rate of the 1- and 2-GPU runs: every rank's staging buffer sat wherever its process happened to start, so half of
+    the uploads crossed the socket interconnect.  Returns a short description for the JSON line (None: nothing done)."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo_, _, hi_ = part.partition("-")
+            cpus.update(range(int(lo_), int(hi_ or lo_) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"gpu": bdf, "numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -316,6 +341,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: linear_operator_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
@@ -414,6 +440,8 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, torch, dist, world, dev, K, d, rhs, step, barrier)
+        if e2e is not None:
+            e2e["host_numa_binding"] = numa  # rank 0's; every rank binds to its own GPU's node
 
     # ---- roofline of the dominant kernel ----
     peaks = {}
@@ -500,7 +528,8 @@ def run_e2e(args, torch, dist, world, dev, K, d, rhs, step, barrier):
     # Upload and compute are pipelined over batch chunks (batch elements are independent): all H2D copies are queued
     # on a copy stream, the compute stream waits for chunk c's event, runs the public API call on that chunk and queues
     # the D2H of its results.  PCIe is the bottleneck (102 GB per step), the solver hides behind it.
-    nchunk = 8 if B % 8 == 0 and B >= 64 else 1
+    # 16 chunks: the solve of the last chunk is the only compute that is not hidden behind the upload
+    nchunk = 16 if B % 16 == 0 and B >= 256 else (8 if B % 8 == 0 and B >= 64 else 1)
     cb = B // nchunk
     copy_stream = torch.cuda.Stream(device=dev)
     dd_dev = torch.empty_like(d)
