@@ -1,3 +1,5 @@
+"""One symmetric Toeplitz product at BASELINE config 4's shape (N = 2^20, 33 columns, batch 16): CUDA-event time; run it under
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum for the per-kernel breakdown."""
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
 from linear_operator_b200 import _kernels

@@ -66,6 +66,14 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert lib.lob_dense_matmul_workspace_bytes(0, 1024, 5000, 5000, 33) == 1024 * 96 * 5000 * 4  # pair kernel: 4 h rows, h = 24
     assert lib.lob_dense_matmul_workspace_bytes(1, 1024, 5000, 5000, 33) == 0
     assert lib.lob_dense_matmul_workspace_bytes(0, 2, 100, 100, 65) == 0
+    # Toeplitz column-pair path: sizes and NULL pointers are rejected before anything is launched
+    assert lib.lob_toeplitz_colmax(0, 0, 8, 3, None, None, None) == -1
+    assert lib.lob_toeplitz_pack(0, 1, 8, 3, 4, None, None, None, None) == -1  # L < N
+    assert b"bad sizes" in lib.lob_last_error()
+    assert lib.lob_toeplitz_pack(0, 1, 8, 3, 16, None, None, None, None) == -1
+    assert b"NULL" in lib.lob_last_error()
+    assert lib.lob_toeplitz_mulr(0, 1, 2, 15, None, 0, None, None) == -1  # odd transform length
+    assert lib.lob_toeplitz_unpack(0, 1, 8, 3, 16, None, 1.0, None, None, None, 0, 0, None, None) == -1
 
 
 def test_lanczos_host_checks_and_no_cpu_fallback():
