@@ -7,6 +7,8 @@ namespace lob {
 
 // z[b,n,s] = z_root[b,n,s] + sqrt(d[b,n]) * eps[s,b,n]; per-tile column sums of squares.
 // 32 x 32 (n x s) tiles through shared memory so both the (S,B,N) read and the (B,N,S) write are coalesced.
+constexpr int PROBE_TILES = 32;  // 32-row tiles per CTA of k_probe_combine
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_probe_combine(int64_t B, int64_t N, int64_t S, const T* __restrict__ z_root, const T* __restrict__ eps,
@@ -15,25 +17,32 @@ k_probe_combine(int64_t B, int64_t N, int64_t S, const T* __restrict__ z_root, c
   __shared__ T tile[32][33];
   __shared__ double red[8][32];
   const int64_t b = blockIdx.z;
-  const int64_t n0 = (int64_t)blockIdx.x * 32, s0 = (int64_t)blockIdx.y * 32;
+  const int64_t s0 = (int64_t)blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;
-  for (int sl = ty; sl < 32; sl += 8) {
-    const int64_t s = s0 + sl, n = n0 + tx;
-    tile[sl][tx] = (s < S && n < N) ? eps[(s * B + b) * N + n] : (T)0;
-  }
-  __syncthreads();
-  double acc = 0.0;
   const int64_t s = s0 + tx;
-  for (int nl = ty; nl < 32; nl += 8) {
-    const int64_t n = n0 + nl;
-    if (s < S && n < N) {
-      T v = tile[tx][nl];
-      if (d) v = v * (T)sqrt((double)d[b * d_bs + n * d_st]);
-      const int64_t idx = (b * N + n) * S + s;
-      if (z_root) v = z_root[idx] + v;
-      z[idx] = v;
-      acc += (double)v * (double)v;
+  double acc = 0.0;
+  // PROBE_TILES 32-row tiles per CTA: one partial sum per column and CTA (a partial per tile made the norm kernel add
+  // N / 32 numbers per column one after the other: 7 of the 7.4 ms of this entry point at N = 10^6)
+  for (int t = 0; t < PROBE_TILES; ++t) {
+    const int64_t n0 = ((int64_t)blockIdx.x * PROBE_TILES + t) * 32;
+    if (n0 >= N) break;
+    for (int sl = ty; sl < 32; sl += 8) {
+      const int64_t ss = s0 + sl, n = n0 + tx;
+      tile[sl][tx] = (ss < S && n < N) ? eps[(ss * B + b) * N + n] : (T)0;
     }
+    __syncthreads();
+    for (int nl = ty; nl < 32; nl += 8) {
+      const int64_t n = n0 + nl;
+      if (s < S && n < N) {
+        T v = tile[tx][nl];
+        if (d) v = v * (T)sqrt((double)d[b * d_bs + n * d_st]);
+        const int64_t idx = (b * N + n) * S + s;
+        if (z_root) v = z_root[idx] + v;
+        z[idx] = v;
+        acc += (double)v * (double)v;
+      }
+    }
+    __syncthreads();
   }
   red[ty][tx] = acc;
   __syncthreads();
@@ -44,14 +53,23 @@ k_probe_combine(int64_t B, int64_t N, int64_t S, const T* __restrict__ z_root, c
   }
 }
 
+// norms[b, s] = sqrt(sum_k parts[b, k, s]); block (32, 8), grid (ceil(S / 32), B): eight partial sums per column, fixed order
 template <typename T>
-__global__ void k_probe_norms(int64_t BS, int64_t S, int ntn, const double* __restrict__ parts, T* __restrict__ norms) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= BS) return;
-  const int64_t b = i / S, s = i % S;
+__global__ void k_probe_norms(int64_t S, int ntn, const double* __restrict__ parts, T* __restrict__ norms) {
+  __shared__ double red[8][32];
+  const int64_t b = blockIdx.y;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t s = (int64_t)blockIdx.x * 32 + tx;
   double t = 0.0;
-  for (int k = 0; k < ntn; ++k) t += parts[(b * ntn + k) * S + s];
-  norms[i] = (T)sqrt(t);
+  if (s < S)
+    for (int k = ty; k < ntn; k += 8) t += parts[(b * ntn + k) * S + s];
+  red[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && s < S) {
+    double a = 0.0;
+    for (int i = 0; i < 8; ++i) a += red[i][tx];
+    norms[b * S + s] = (T)sqrt(a);
+  }
 }
 
 template <typename T>
@@ -137,7 +155,7 @@ extern "C" int lob_probe_assemble(int32_t dtype, int64_t B, int64_t N, int64_t S
   LOB_REQUIRE(B <= 65535, "lob_probe_assemble: flattened batch > 65535 not supported");
   LOB_REQUIRE(eps_diag && probes && norms && ws, "lob_probe_assemble: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  const int ntn = (int)cdiv(N, 32);
+  const int ntn = (int)cdiv(N, 32 * PROBE_TILES);
   dim3 grid((unsigned)ntn, (unsigned)cdiv(S, 32), (unsigned)B);
   const int64_t total = B * N * S;
   LOB_DISPATCH_DTYPE(dtype, {
@@ -146,8 +164,8 @@ extern "C" int lob_probe_assemble(int32_t dtype, int64_t B, int64_t N, int64_t S
                                                             d_batch_stride, d_stride, (scalar_t*)probes, (double*)ws,
                                                             ntn);
     LOB_TRY(check_launch("k_probe_combine"));
-    k_probe_norms<scalar_t><<<(unsigned)cdiv(B * S, 256), 256, 0, st>>>(B * S, S, ntn, (const double*)ws,
-                                                                       (scalar_t*)norms);
+    k_probe_norms<scalar_t><<<dim3((unsigned)cdiv(S, 32), (unsigned)B), dim3(32, 8), 0, st>>>(
+        S, ntn, (const double*)ws, (scalar_t*)norms);
     LOB_TRY(check_launch("k_probe_norms"));
     k_probe_normalize<scalar_t><<<(unsigned)cdiv(total, 256), 256, 0, st>>>(N, S, (scalar_t*)probes,
                                                                            (const scalar_t*)norms, total);
