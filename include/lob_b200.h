@@ -250,7 +250,13 @@ int lob_toeplitz_embed(int32_t dtype, int64_t B, int64_t N, int64_t L, const voi
 int lob_toeplitz_mul(int32_t dtype, int64_t B, int64_t C, int64_t H, const void* fc, int64_t fc_batch_stride, void* fx,
                      void* stream);
 int lob_toeplitz_unpad(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* yt, double scale,
-                       const void* X, const void* d, int64_t d_batch_stride, int64_t d_stride, void* Y, void* stream);
+                       const void* X, const void* d, int64_t d_batch_stride, int64_t d_stride, void* Y, double* dots,
+                       void* stream);
+/* dots (optional, both unpad and unpack): (B, parts, C) partial sums of X * Y per row block and column -- linear_cg's
+ * <p, A p> (linear_cg.py:250-251) out of the last pass of the product; parts = lob_toeplitz_unpad_parts() (0: this
+ * column count has no fused form) resp. lob_toeplitz_unpack_parts(). */
+int32_t lob_toeplitz_unpad_parts(int32_t dtype, int64_t N, int64_t C);
+int32_t lob_toeplitz_unpack_parts(int64_t N);
 /* The same product through complex FFTs of column PAIRS (the symmetric embedding has a real spectrum, so two real
  * columns ride one C2C transform: no real-to-complex pre/post-processing passes, transposes folded into pack/unpack).
  * colmax: maxbits (B, C) = bit patterns of max_n |X| (uint32 / uint64);  pack: zt (B, ceil(C/2), L) complex =
@@ -263,7 +269,7 @@ int lob_toeplitz_mulr(int32_t dtype, int64_t B, int64_t P, int64_t L, const void
                       void* stream);
 int lob_toeplitz_unpack(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* zt, double scale,
                         const void* maxbits, const void* X, const void* d, int64_t d_batch_stride, int64_t d_stride,
-                        void* Y, void* stream);
+                        void* Y, double* dots, void* stream);
 
 /* generic batched small-K product  Y (B, M, C) = A (B|1, M, K) X (B, K, C): Q t, L eps, U w
  * (added_diag_linear_operator.py:137, _linear_operator.py:2784-2791, low_rank_root_added_diag_...py:83).

@@ -557,7 +557,7 @@ def _kron_tensor_core_ok(factors, X) -> bool:
     return int(math.prod(sizes)) == X.shape[-2]
 
 
-def _kron_matmul_tc(factors, X, d):
+def _kron_matmul_tc(factors, X, d, want_dots=False):
     """(K1 (x) ... (x) Km) X (+ d (.) X) as a chain of tensor-core GEMMs (csrc/gemm3x.cu) on column planes.
 
     The vector block X (B, N, C) has C = 33 columns: a slab with a 33-element leading dimension is not TMA-addressable,
@@ -579,6 +579,9 @@ def _kron_matmul_tc(factors, X, d):
     sizes = [int(f.shape[-1]) for f in factors]
     dd, d_bs, d_st = _diag_args(d, batch_shape, N)
     Y = torch.empty(B, N, C, dtype=X.dtype, device=X.device)
+    # linear_cg's <p, A p> out of the chain's last pass (it holds both X and Y): one partial sum per row block, column
+    n_parts = int(lib.lob_toeplitz_unpad_parts(dt(X), N, C)) if want_dots else 0
+    dots = torch.empty(B, n_parts, C, dtype=torch.float64, device=X.device) if n_parts else None
     # batch chunks keep every mode's GEMM batch (B * C * pre) inside the launch limit
     max_pre = int(math.prod(sizes[:-2])) if len(sizes) > 2 else 1
     bchunk = max(1, min(B, 65535 // (C * max_pre)))
@@ -606,20 +609,22 @@ def _kron_matmul_tc(factors, X, d):
         dd_c = dd if (dd is None or d_bs == 0) else dd[b0:b1]
         check(
             lib.lob_toeplitz_unpad(dt(X), nb, N, C, N, ptr(cur), 1.0, ptr(Xf[b0:b1]), ptr(dd_c), d_bs, d_st,
-                                   ptr(Y[b0:b1]), stream(X)),
+                                   ptr(Y[b0:b1]), ptr(dots[b0:b1]) if dots is not None else None, stream(X)),
             "lob_toeplitz_unpad",
         )
-    return Y.reshape(*batch_shape, N, C)
+    Y = Y.reshape(*batch_shape, N, C)
+    return (Y, dots, n_parts) if want_dots else Y
 
 
-def kron_matmul(factors: Sequence[torch.Tensor], X: torch.Tensor, d: Optional[torch.Tensor] = None) -> torch.Tensor:
+def kron_matmul(factors: Sequence[torch.Tensor], X: torch.Tensor, d: Optional[torch.Tensor] = None,
+                want_dots: bool = False):
     """(K1 (x) K2 (x) ...) X (+ d (.) X)  (kronecker_product_linear_operator.py:34-45; added_diag_linear_operator.py
     :72-76 for the fused diagonal).  fp32 operators with TMA-addressable factors run as a tensor-core GEMM chain
     (``_kron_matmul_tc``); everything else (fp64, odd factor sizes) as one fused CUDA-core mode product per factor."""
     require_cuda(X, d, *factors)
     lib = _lib.load()
     if _kron_tensor_core_ok(factors, X):
-        return _kron_matmul_tc(factors, X, d)
+        return _kron_matmul_tc(factors, X, d, want_dots)
     batch_shape = torch.broadcast_shapes(X.shape[:-2], *[f.shape[:-2] for f in factors])
     B = _numel(batch_shape)
     Ntot, C = X.shape[-2:]
@@ -640,7 +645,7 @@ def kron_matmul(factors: Sequence[torch.Tensor], X: torch.Tensor, d: Optional[to
     cur = cur.reshape(*batch_shape, Ntot, C)
     if d is not None:
         cur = cur.add_(scale_rows(X.expand(*batch_shape, Ntot, C), d, "mul"))
-    return cur
+    return (cur, None, 0) if want_dots else cur  # no fused <X, Y> on the CUDA-core mode kernels: linear_cg adds its own
 
 
 def _next_pow2(n: int) -> int:
@@ -663,10 +668,12 @@ def toeplitz_embed_fft(col: torch.Tensor):
 TOEPLITZ_SCRATCH_BYTES = 4.5 * 2**30  # per (B, C, L) scratch array of one batch chunk of toeplitz_matmul
 
 
-def toeplitz_matmul(col: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = None, fc_cache=None):
+def toeplitz_matmul(col: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = None, fc_cache=None,
+                    want_dots: bool = False):
     """Symmetric Toeplitz matmul through a length-L (power of two >= 2N) real circulant embedding
     (utils/toeplitz.py:131-149 uses length 2N-1 complex FFTs; any L >= 2N-1 gives the same product).
-    Optionally fuses + d (.) X."""
+    Optionally fuses + d (.) X; ``want_dots``: returns ``(Y, dots, n_parts)`` with the (B, n_parts, C) partial sums of
+    X * Y out of the unpack pass (linear_cg's <p, A p>)."""
     require_cuda(col, X, d)
     lib = _lib.load()
     N, C = X.shape[-2:]
@@ -689,6 +696,8 @@ def toeplitz_matmul(col: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor
     # (csrc/structured.cu, "complex FFTs of column pairs").  Scratch: two (B, ceil(C/2), L) complex arrays (transform
     # input and output) -- 2 x 17.8 GB at BASELINE config 4 (B = 64, N = 2^20, 33 columns) -- so the product runs in
     # batch chunks whose arrays stay below ~4.5 GB each (16 elements at config 4); batch elements are independent.
+    n_parts = int(lib.lob_toeplitz_unpack_parts(N)) if want_dots else 0
+    dots = torch.empty(B, n_parts, C, dtype=torch.float64, device=X.device) if n_parts else None
     fr = fc.real.contiguous()  # (B | 1, L / 2 + 1)
     fr_bs = 0 if fc_bs == 0 else fr.shape[-1]
     P = (C + 1) // 2
@@ -714,11 +723,12 @@ def toeplitz_matmul(col: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor
         dd_c = dd if (dd is None or d_bs == 0) else dd[b0:b1]
         check(
             lib.lob_toeplitz_unpack(dt(X), nb, N, C, L, ptr(zt), 1.0 / L, ptr(maxbits), ptr(xs), ptr(dd_c), d_bs, d_st,
-                                    ptr(Y[b0:b1]), stream(X)),
+                                    ptr(Y[b0:b1]), ptr(dots[b0:b1]) if dots is not None else None, stream(X)),
             "lob_toeplitz_unpack",
         )
         del zt
-    return Y.reshape(*batch_shape, N, C)
+    Y = Y.reshape(*batch_shape, N, C)
+    return (Y, dots, n_parts) if want_dots else Y
 
 
 def cap_solve(G: torch.Tensor, W: torch.Tensor):

@@ -175,7 +175,7 @@ k_planes_in(int64_t N, int64_t C, int64_t L, int rows, const T* __restrict__ X, 
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_planes_out(int64_t N, int64_t C, int64_t L, int rows, const T* __restrict__ yt, T scale, const T* __restrict__ X,
-             const T* __restrict__ d, int64_t d_bs, int64_t d_st, T* __restrict__ Y) {
+             const T* __restrict__ d, int64_t d_bs, int64_t d_st, T* __restrict__ Y, double* __restrict__ dots) {
   extern __shared__ __align__(16) unsigned char pl_smem[];
   T* tile = reinterpret_cast<T*>(pl_smem);
   const int ld = (int)C | 1;
@@ -191,11 +191,23 @@ k_planes_out(int64_t N, int64_t C, int64_t L, int rows, const T* __restrict__ yt
   int r = tid / (int)C, c = tid - r * (int)C;
   for (int e = tid; e < valid * (int)C; e += 256) {
     T v = scale * tile[r * ld + c];
-    if (d) v += d[b * d_bs + (n0 + r) * d_st] * X[base + e];
+    const T x = (d || dots) ? X[base + e] : (T)0;
+    if (d) v += d[b * d_bs + (n0 + r) * d_st] * x;
     Y[base + e] = v;
+    if (dots) tile[r * ld + c] = x * v;  // this thread's own element: no hazard
     r += dq;
     c += dr;
     if (c >= (int)C) { c -= (int)C; ++r; }
+  }
+  if (dots) {
+    // partial <X, Y> of this row block per column (linear_cg.py:250-251 fused into the last pass of the product)
+    __syncthreads();
+    for (int cc = warp; cc < C; cc += 8) {
+      double a = 0.0;
+      for (int l = lane; l < valid; l += 32) a += (double)tile[l * ld + cc];
+      a = warp_sum(a);
+      if (lane == 0) dots[(b * gridDim.x + blockIdx.x) * C + cc] = a;
+    }
   }
 }
 
@@ -338,7 +350,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_toeplitz_unpack(int64_t N, int64_t C, int64_t L, const typename PairOf<T>::type* __restrict__ zt, T scale,
                   const typename PairOf<T>::bits* __restrict__ maxbits, const T* __restrict__ X,
-                  const T* __restrict__ d, int64_t d_bs, int64_t d_st, T* __restrict__ Y) {
+                  const T* __restrict__ d, int64_t d_bs, int64_t d_st, T* __restrict__ Y, double* __restrict__ dots) {
   using T2 = typename PairOf<T>::type;
   extern __shared__ __align__(16) unsigned char tp_smem[];
   T* tile = reinterpret_cast<T*>(tp_smem);
@@ -365,11 +377,23 @@ k_toeplitz_unpack(int64_t N, int64_t C, int64_t L, const typename PairOf<T>::typ
   int r = tid / (int)C, c = tid - r * (int)C;
   for (int e = tid; e < rows * (int)C; e += 256) {
     T v = tile[r * ld + c] * sc[c];
-    if (d) v += d[b * d_bs + (n0 + r) * d_st] * X[base + e];
+    const T x = (d || dots) ? X[base + e] : (T)0;
+    if (d) v += d[b * d_bs + (n0 + r) * d_st] * x;
     Y[base + e] = v;
+    if (dots) tile[r * ld + c] = x * v;
     r += dq;
     c += dr;
     if (c >= (int)C) { c -= (int)C; ++r; }
+  }
+  if (dots) {
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int cc = warp; cc < C; cc += 8) {
+      double a = 0.0;
+      for (int l = lane; l < rows; l += 32) a += (double)tile[l * ld + cc];
+      a = warp_sum(a);
+      if (lane == 0) dots[(b * gridDim.x + blockIdx.x) * C + cc] = a;
+    }
   }
 }
 
@@ -564,12 +588,14 @@ extern "C" int lob_toeplitz_mulr(int32_t dtype, int64_t B, int64_t P, int64_t L,
   });
 }
 
+extern "C" int32_t lob_toeplitz_unpack_parts(int64_t N) { return (int32_t)cdiv(N, TP_ROWS); }
+
 extern "C" int lob_toeplitz_unpack(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* zt,
                                    double scale, const void* maxbits, const void* X, const void* d,
-                                   int64_t d_batch_stride, int64_t d_stride, void* Y, void* stream) {
+                                   int64_t d_batch_stride, int64_t d_stride, void* Y, double* dots, void* stream) {
   LOB_REQUIRE(B > 0 && N > 0 && C > 0 && L >= N, "lob_toeplitz_unpack: bad sizes");
   LOB_REQUIRE(B <= 65535 && C <= 4096, "lob_toeplitz_unpack: flattened batch > 65535 or more than 4096 columns not supported");
-  LOB_REQUIRE(zt && maxbits && Y && (!d || X), "lob_toeplitz_unpack: NULL pointer");
+  LOB_REQUIRE(zt && maxbits && Y && ((!d && !dots) || X), "lob_toeplitz_unpack: NULL pointer");
   dim3 grid((unsigned)cdiv(N, TP_ROWS), (unsigned)B);
   LOB_DISPATCH_DTYPE(dtype, {
     const size_t smem = sizeof(scalar_t) * ((size_t)TP_ROWS * ((int)C | 1) + C);
@@ -577,17 +603,24 @@ extern "C" int lob_toeplitz_unpack(int32_t dtype, int64_t B, int64_t N, int64_t 
     k_toeplitz_unpack<scalar_t><<<grid, 256, smem, (cudaStream_t)stream>>>(
         N, C, L, (const typename PairOf<scalar_t>::type*)zt, (scalar_t)scale,
         (const typename PairOf<scalar_t>::bits*)maxbits, (const scalar_t*)X, (const scalar_t*)d, d_batch_stride,
-        d_stride, (scalar_t*)Y);
+        d_stride, (scalar_t*)Y, dots);
     return check_launch("k_toeplitz_unpack");
   });
 }
 
+// row blocks (= partial <X, Y> sums per column) of lob_toeplitz_unpad; 0: this shape takes the tile kernel, no dots
+extern "C" int32_t lob_toeplitz_unpad_parts(int32_t dtype, int64_t N, int64_t C) {
+  const int rows = planes_rows(C, dsize(dtype));
+  return rows ? (int32_t)cdiv(N, rows) : 0;
+}
+
 extern "C" int lob_toeplitz_unpad(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* yt,
                                   double scale, const void* X, const void* d, int64_t d_batch_stride, int64_t d_stride,
-                                  void* Y, void* stream) {
+                                  void* Y, double* dots, void* stream) {
   LOB_REQUIRE(B > 0 && N > 0 && C > 0 && L >= N, "lob_toeplitz_unpad: bad sizes");
   LOB_REQUIRE(B <= 65535, "lob_toeplitz_unpad: flattened batch > 65535 not supported");
-  LOB_REQUIRE(yt && Y && (!d || X), "lob_toeplitz_unpad: NULL pointer");
+  LOB_REQUIRE(yt && Y && ((!d && !dots) || X), "lob_toeplitz_unpad: NULL pointer");
+  LOB_REQUIRE(!dots || planes_rows(C, dsize(dtype)) > 0, "lob_toeplitz_unpad: no fused dots for this column count");
   dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(C, 32), (unsigned)B);
   LOB_DISPATCH_DTYPE(dtype, {
     const int rows = planes_rows(C, sizeof(scalar_t));
@@ -595,7 +628,7 @@ extern "C" int lob_toeplitz_unpad(int32_t dtype, int64_t B, int64_t N, int64_t C
       const size_t smem = sizeof(scalar_t) * (size_t)rows * ((int)C | 1);
       k_planes_out<scalar_t><<<dim3((unsigned)cdiv(N, rows), (unsigned)B), 256, smem, (cudaStream_t)stream>>>(
           N, C, L, rows, (const scalar_t*)yt, (scalar_t)scale, (const scalar_t*)X, (const scalar_t*)d, d_batch_stride,
-          d_stride, (scalar_t*)Y);
+          d_stride, (scalar_t*)Y, dots);
       return check_launch("k_planes_out");
     }
     k_toeplitz_unpad<scalar_t><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(

@@ -98,6 +98,15 @@ class AddedDiagLinearOperator(SumLinearOperator):
             closure.fused = lambda v: _kernels.dense_matmul(tsr, v, d=d, want_dots=True)
             closure.graph_spec = (tsr, d)  # small solves replay as one CUDA graph (settings.cuda_graphs)
             return closure
+        fused = getattr(self._linear_op, "_matmul_add_diag", None)
+        if fused is not None:  # Kronecker / Toeplitz: <p, A p> comes out of the product's last pass
+            d = self._diag_tensor._diag
+
+            def closure(v):
+                return fused(v, d)
+
+            closure.fused = lambda v: fused(v, d, want_dots=True)
+            return closure
         return self._matmul
 
     def add_diagonal(self, diag):  # :78-82

@@ -72,9 +72,17 @@ class KroneckerProductLinearOperator(LinearOperator):
             return self.add_diagonal(other._diagonal())
         return super().__add__(other)
 
-    def _matmul_add_diag(self, rhs, diag):
-        """K X + d (.) X with the diagonal folded into the chain's last pass (AddedDiagLinearOperator._matmul)."""
-        return _kernels.kron_matmul(self._factor_tensors(), rhs, d=diag)
+    def _matmul_add_diag(self, rhs, diag, want_dots=False):
+        """K X + d (.) X with the diagonal folded into the chain's last pass (AddedDiagLinearOperator._matmul);
+        ``want_dots``: and linear_cg's partial <X, Y> sums out of the same pass."""
+        return _kernels.kron_matmul(self._factor_tensors(), rhs, d=diag, want_dots=want_dots)
+
+    def _matmul_closure(self):
+        def closure(v):
+            return self._matmul(v)
+
+        closure.fused = lambda v: self._matmul_add_diag(v, None, want_dots=True)
+        return closure
 
     def _transpose_nonbatch(self):
         return self.__class__(*(op._transpose_nonbatch() for op in self.linear_ops))

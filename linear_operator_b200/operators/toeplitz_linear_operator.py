@@ -29,9 +29,17 @@ class ToeplitzLinearOperator(LinearOperator):
         res = _kernels.toeplitz_matmul(self.column, rhs, fc_cache=self._spectrum())
         return res.squeeze(-1) if squeeze else res
 
-    def _matmul_add_diag(self, rhs, diag):
-        """T X + d (.) X with the diagonal folded into the un-padding kernel."""
-        return _kernels.toeplitz_matmul(self.column, rhs, d=diag, fc_cache=self._spectrum())
+    def _matmul_add_diag(self, rhs, diag, want_dots=False):
+        """T X + d (.) X with the diagonal folded into the un-padding kernel (``want_dots``: and linear_cg's partial
+        <X, Y> sums out of the same pass)."""
+        return _kernels.toeplitz_matmul(self.column, rhs, d=diag, fc_cache=self._spectrum(), want_dots=want_dots)
+
+    def _matmul_closure(self):
+        def closure(v):
+            return self._matmul(v)
+
+        closure.fused = lambda v: self._matmul_add_diag(v, None, want_dots=True)
+        return closure
 
     def _bilinear_derivative(self, left_vecs, right_vecs):  # :55-66 -> utils/toeplitz.py:164-204
         if left_vecs.dim() == 1:

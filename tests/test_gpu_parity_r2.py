@@ -252,6 +252,34 @@ def test_toeplitz_matmul_column_pairs_of_very_different_scale():
             assert err <= 2e-5 * ref, f"column {c} (scale {scales[c].item():g}): {err / max(ref, 1e-300):.2e}"  # zero column: exactly 0
 
 
+def test_structured_products_fused_dot_partials():
+    """Kronecker chain and Toeplitz column-pair product hand linear_cg the <X, Y> partial sums of their last pass
+    (linear_cg.py:250-251): they must add up to the dots of the product they come with, ragged row blocks included."""
+    from linear_operator_b200 import _kernels
+
+    gen = torch.Generator(device=DEV).manual_seed(23)
+    fs = []
+    for n in (8, 12, 20):
+        G = torch.randn(2, n, n, device=DEV, generator=gen)
+        fs.append(G @ G.mT / n + 0.1 * torch.eye(n, device=DEV))
+    N, C = 8 * 12 * 20, 33
+    X = torch.randn(2, N, C, device=DEV, generator=gen)
+    d = 0.5 + torch.rand(2, N, device=DEV, generator=gen)
+    Y, dots, n_parts = _kernels.kron_matmul(fs, X, d=d, want_dots=True)
+    assert dots is not None and dots.shape == (2, n_parts, C)
+    assert torch.equal(Y, _kernels.kron_matmul(fs, X, d=d))
+    check(npy(dots.sum(1)), npy((X.double() * Y.double()).sum(-2)), 1e-6)
+    col = torch.exp(-0.5 * (torch.arange(1000, device=DEV) / 9.0) ** 2).repeat(2, 1)
+    Xt = torch.randn(2, 1000, C, device=DEV, generator=gen)
+    for dd in (None, 0.5 + torch.rand(2, 1000, device=DEV, generator=gen)):
+        Yt, dots, n_parts = _kernels.toeplitz_matmul(col, Xt, dd, want_dots=True)
+        assert dots.shape == (2, n_parts, C) and torch.equal(Yt, _kernels.toeplitz_matmul(col, Xt, dd))
+        check(npy(dots.sum(1)), npy((Xt.double() * Yt.double()).sum(-2)), 1e-6)
+    Xd = Xt.double()
+    Yd, dots, _ = _kernels.toeplitz_matmul(col.double(), Xd, None, want_dots=True)
+    check(npy(dots.sum(1)), npy((Xd * Yd).sum(-2)), 1e-13)
+
+
 def test_cfg4_toeplitz_baseline_shape_vs_oracle():
     """BASELINE configs[3]: toeplitz_matmul at N = 2^20 with the full 33-column block, one batch element, fp32, against
     the oracle's length-(2N-1) complex-FFT restatement (utils/toeplitz.py:131-149)."""
