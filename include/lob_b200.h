@@ -254,9 +254,10 @@ int lob_toeplitz_unpad(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L
                        void* stream);
 /* dots (optional, both unpad and unpack): (B, parts, C) partial sums of X * Y per row block and column -- linear_cg's
  * <p, A p> (linear_cg.py:250-251) out of the last pass of the product; parts = lob_toeplitz_unpad_parts() (0: this
- * column count has no fused form) resp. lob_toeplitz_unpack_parts(). */
+ * column count has no fused form) resp. lob_toeplitz_unpack_parts() (0: more columns than one shared-memory tile
+ * holds -- pack / unpack then refuse the call and the caller splits the column block). */
 int32_t lob_toeplitz_unpad_parts(int32_t dtype, int64_t N, int64_t C);
-int32_t lob_toeplitz_unpack_parts(int64_t N);
+int32_t lob_toeplitz_unpack_parts(int32_t dtype, int64_t N, int64_t C);
 /* The same product through complex FFTs of column PAIRS (the symmetric embedding has a real spectrum, so two real
  * columns ride one C2C transform: no real-to-complex pre/post-processing passes, transposes folded into pack/unpack).
  * colmax: maxbits (B, C) = bit patterns of max_n |X| (uint32 / uint64);  pack: zt (B, ceil(C/2), L) complex =

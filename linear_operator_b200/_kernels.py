@@ -696,7 +696,13 @@ def toeplitz_matmul(col: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor
     # (csrc/structured.cu, "complex FFTs of column pairs").  Scratch: two (B, ceil(C/2), L) complex arrays (transform
     # input and output) -- 2 x 17.8 GB at BASELINE config 4 (B = 64, N = 2^20, 33 columns) -- so the product runs in
     # batch chunks whose arrays stay below ~4.5 GB each (16 elements at config 4); batch elements are independent.
-    n_parts = int(lib.lob_toeplitz_unpack_parts(N)) if want_dots else 0
+    rows_parts = int(lib.lob_toeplitz_unpack_parts(dt(X), N, C))
+    if rows_parts == 0:
+        # more columns than one shared-memory tile of the pack / unpack kernels holds: column blocks of 64
+        outs = [toeplitz_matmul(col, X[..., c0:c0 + 64].contiguous(), d, fc_cache=(fc, L)) for c0 in range(0, C, 64)]
+        Yc = torch.cat(outs, dim=-1)
+        return (Yc, None, 0) if want_dots else Yc
+    n_parts = rows_parts if want_dots else 0
     dots = torch.empty(B, n_parts, C, dtype=torch.float64, device=X.device) if n_parts else None
     fr = fc.real.contiguous()  # (B | 1, L / 2 + 1)
     fr_bs = 0 if fc_bs == 0 else fr.shape[-1]

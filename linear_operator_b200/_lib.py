@@ -152,7 +152,7 @@ _SIGS = {
         [c_int32, c_int64, c_int64, c_int64, c_int64, _P, c_double, _P, _P, c_int64, c_int64, _P, _P, _P],
     ),
     "lob_toeplitz_unpad_parts": (c_int32, [c_int32, c_int64, c_int64]),
-    "lob_toeplitz_unpack_parts": (c_int32, [c_int64]),
+    "lob_toeplitz_unpack_parts": (c_int32, [c_int32, c_int64, c_int64]),
     "lob_cap_solve_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int64]),
     "lob_cap_solve": (ctypes.c_int, [c_int32, c_int64, c_int32, c_int64, _P, c_int64, _P, _P, _P, _P, _P]),
     "lob_gemm3x_splits": (c_int32, [c_int64, c_int64, c_int64, c_int64, c_int32]),

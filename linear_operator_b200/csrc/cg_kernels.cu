@@ -10,6 +10,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <initializer_list>
 
 #include "common.cuh"
 
@@ -55,7 +56,7 @@ static CgLayout cg_layout(const lob_cg_params* p) {
     if (eff >= 0.97 || c >= 8 * cdiv(2 * slots, p->B)) break;
   }
   if (best_eff < 0) nch = maxch;  // fewer rows than two waves' worth: as many chunks as the rows allow
-  L.rows_per_chunk = cdiv(p->N, nch);
+  L.rows_per_chunk = (cdiv(p->N, nch) + 3) / 4 * 4;  // whole groups of four rows: the float4 kernels' unit
   L.nchunks = (int)cdiv(p->N, L.rows_per_chunk);
   const size_t bc = (size_t)p->B * p->C;
   const size_t bs = (size_t)p->B * (p->n_tridiag > 0 ? p->n_tridiag : 1);
@@ -401,6 +402,202 @@ __global__ void k_step_p(Dims d, const T* __restrict__ z, T* __restrict__ pvec, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// float4 forms of the two per-iteration vector kernels (fp32, C <= 128, N * C % 4 == 0, 16-byte aligned vectors).
+// A group of four rows is C consecutive float4s; thread (tx, ty) always takes float4 tx of the groups ty, ty + ry, ...:
+// its four lanes are the FIXED columns (4 tx + i) mod C, so the per-column scalars sit in four registers and the
+// per-column partial sums in four accumulators.  Four times the bytes in flight per load instruction of the scalar
+// kernels, which ran at 4.4 - 4.8 TB/s where a plain float4 stream of the same shape reaches 6.5 (scripts/
+// stream_width_bench.cu).  Same arithmetic per element as k_step_xr / k_step_p; the per-column sums are added in a
+// different (still fixed) order.
+// ---------------------------------------------------------------------------------------------------------------
+struct V4Map {
+  int c[4];   // column of lane i
+  int dr[4];  // row of lane i inside the group of four
+};
+__device__ __forceinline__ V4Map v4_map(int tx, int C) {
+  V4Map m;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int f = 4 * tx + i;
+    m.dr[i] = f / C;
+    m.c[i] = f - m.dr[i] * C;
+  }
+  return m;
+}
+// column sums of per-lane accumulators: red[(ty * C + tx) * 4 + i]; column c collects the lanes at flat positions
+// c, c + C, c + 2 C, c + 3 C of the group, over all ty -- fixed order
+__device__ __forceinline__ double v4_column_sum(const double* red, int c, int C, int ry) {
+  double s = 0.0;
+  for (int m = 0; m < 4; ++m) {
+    const int f = c + m * C;
+    for (int i = 0; i < ry; ++i) s += red[(i * C + (f >> 2)) * 4 + (f & 3)];
+  }
+  return s;
+}
+
+__global__ void k_step_xr_v4(Dims d, const float* __restrict__ ap, const float* __restrict__ pvec, float* __restrict__ x,
+                             float* __restrict__ r, const double* __restrict__ pap_parts, int n_pap_parts,
+                             const double* __restrict__ rz, const uint8_t* __restrict__ conv,
+                             double* __restrict__ alpha_out, double* __restrict__ parts_rr, lob_cg_status* status,
+                             double eps, int check_nan) {
+  if (status->stop) return;
+  extern __shared__ double red[];  // [ry][C][4] doubles, then C floats (alpha)
+  const int64_t b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int C = (int)d.C, tx = threadIdx.x, ty = threadIdx.y, ry = blockDim.y;
+  float* alpha_s = reinterpret_cast<float*>(red + (size_t)ry * C * 4);
+  const int64_t row0 = (int64_t)chunk * d.rows_per_chunk;
+  const int64_t nrows = min(row0 + d.rows_per_chunk, d.N) - row0;
+  if (ty == 0) {
+    // alpha = rz / <p,Ap>; denominator < eps -> 0; converged columns -> 0  (as k_step_xr)
+    const float den = (float)sum_parts(pap_parts, b, n_pap_parts, C, tx);
+    float a = (den < (float)eps) ? 0.f : (float)((float)rz[b * C + tx] / den);
+    if (conv[b * C + tx]) a = 0.f;
+    if (chunk == 0) alpha_out[b * C + tx] = (double)a;
+    alpha_s[tx] = a;
+  }
+  __syncthreads();
+  const V4Map m = v4_map(tx, C);
+  float a[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = alpha_s[m.c[i]];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  bool saw_nan = false;
+  const int64_t base = (b * d.N + row0) * C;  // multiple of 4 elements (launcher)
+  const int64_t ngroups = (nrows + 3) / 4;
+  const float4* ap4 = reinterpret_cast<const float4*>(ap + base);
+  const float4* p4 = reinterpret_cast<const float4*>(pvec + base);
+  float4* r4 = reinterpret_cast<float4*>(r + base);
+  float4* x4 = reinterpret_cast<float4*>(x + base);
+  const int64_t full = nrows / 4;  // groups whose four rows all exist
+  int64_t g = ty;
+  for (; g + ry < full; g += 2 * ry) {
+    const int64_t i0 = g * C + tx, i1 = (g + ry) * C + tx;
+    const float4 q0 = ap4[i0], q1 = ap4[i1], rr0 = r4[i0], rr1 = r4[i1], pp0 = p4[i0], pp1 = p4[i1], xx0 = x4[i0],
+                 xx1 = x4[i1];
+    float qv[2][4] = {{q0.x, q0.y, q0.z, q0.w}, {q1.x, q1.y, q1.z, q1.w}};
+    float rv[2][4] = {{rr0.x, rr0.y, rr0.z, rr0.w}, {rr1.x, rr1.y, rr1.z, rr1.w}};
+    float pv[2][4] = {{pp0.x, pp0.y, pp0.z, pp0.w}, {pp1.x, pp1.y, pp1.z, pp1.w}};
+    float xv[2][4] = {{xx0.x, xx0.y, xx0.z, xx0.w}, {xx1.x, xx1.y, xx1.z, xx1.w}};
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (check_nan) saw_nan |= (qv[u][i] != qv[u][i]);
+        rv[u][i] -= a[i] * qv[u][i];
+        xv[u][i] += a[i] * pv[u][i];
+        acc[i] += (double)rv[u][i] * (double)rv[u][i];
+      }
+    r4[i0] = make_float4(rv[0][0], rv[0][1], rv[0][2], rv[0][3]);
+    r4[i1] = make_float4(rv[1][0], rv[1][1], rv[1][2], rv[1][3]);
+    x4[i0] = make_float4(xv[0][0], xv[0][1], xv[0][2], xv[0][3]);
+    x4[i1] = make_float4(xv[1][0], xv[1][1], xv[1][2], xv[1][3]);
+  }
+  for (; g < ngroups; g += ry) {
+    if (g < full) {
+      const int64_t i0 = g * C + tx;
+      const float4 q0 = ap4[i0], rr0 = r4[i0], pp0 = p4[i0], xx0 = x4[i0];
+      float qv[4] = {q0.x, q0.y, q0.z, q0.w}, rv[4] = {rr0.x, rr0.y, rr0.z, rr0.w};
+      float pv[4] = {pp0.x, pp0.y, pp0.z, pp0.w}, xv[4] = {xx0.x, xx0.y, xx0.z, xx0.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (check_nan) saw_nan |= (qv[i] != qv[i]);
+        rv[i] -= a[i] * qv[i];
+        xv[i] += a[i] * pv[i];
+        acc[i] += (double)rv[i] * (double)rv[i];
+      }
+      r4[i0] = make_float4(rv[0], rv[1], rv[2], rv[3]);
+      x4[i0] = make_float4(xv[0], xv[1], xv[2], xv[3]);
+    } else {  // the ragged last group (N % 4 rows): element by element
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (g * 4 + m.dr[i] < nrows) {
+          const int64_t e = base + (g * 4 + m.dr[i]) * C + m.c[i];
+          const float q = ap[e];
+          if (check_nan) saw_nan |= (q != q);
+          const float rn = r[e] - a[i] * q;
+          r[e] = rn;
+          x[e] = x[e] + a[i] * pvec[e];
+          acc[i] += (double)rn * (double)rn;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) red[(ty * C + tx) * 4 + i] = acc[i];
+  __syncthreads();
+  if (ty == 0) parts_rr[(b * d.nchunks + chunk) * C + tx] = v4_column_sum(red, tx, C, ry);
+  if (saw_nan) atomicOr(&status->nan_detected, 1);
+}
+
+__global__ void k_step_p_v4(Dims d, const float* __restrict__ z, float* __restrict__ pvec,
+                            const double* __restrict__ parts_rz, int n_rz_parts, const double* __restrict__ parts_rr,
+                            const double* __restrict__ rz_old, double* __restrict__ rz_new, double* __restrict__ beta_out,
+                            double* __restrict__ resid, uint8_t* __restrict__ conv, const uint8_t* __restrict__ rhs_zero,
+                            const lob_cg_status* status, double eps, double sua) {
+  if (status->stop) return;
+  extern __shared__ double red[];
+  const int64_t b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int C = (int)d.C, tx = threadIdx.x, ty = threadIdx.y, ry = blockDim.y;
+  float* beta_s = reinterpret_cast<float*>(red);
+  const int64_t row0 = (int64_t)chunk * d.rows_per_chunk;
+  const int64_t nrows = min(row0 + d.rows_per_chunk, d.N) - row0;
+  if (ty == 0) {  // beta, residual norm, converged flags (as k_step_p)
+    const float rzn = (float)sum_parts(parts_rz, b, n_rz_parts, C, tx);
+    const float rzo = (float)rz_old[b * C + tx];
+    const float be = (rzo < (float)eps) ? 0.f : (float)(rzn / rzo);
+    beta_s[tx] = be;
+    if (chunk == 0) {
+      const int64_t i = b * C + tx;
+      rz_new[i] = (double)rzn;
+      beta_out[i] = (double)be;
+      float nrm = (float)sqrt(sum_parts(parts_rr, b, d.nchunks, C, tx));
+      if (rhs_zero[i]) nrm = 0.f;
+      resid[i] = (double)nrm;
+      conv[i] = (nrm < (float)sua) ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  const V4Map m = v4_map(tx, C);
+  float be[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) be[i] = beta_s[m.c[i]];
+  const int64_t base = (b * d.N + row0) * C;
+  const int64_t ngroups = (nrows + 3) / 4, full = nrows / 4;
+  const float4* z4 = reinterpret_cast<const float4*>(z + base);
+  float4* p4 = reinterpret_cast<float4*>(pvec + base);
+  int64_t g = ty;
+  for (; g + 3 * ry < full; g += 4 * ry) {
+    float4 zz[4], pp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      zz[u] = z4[(g + u * ry) * C + tx];
+      pp[u] = p4[(g + u * ry) * C + tx];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      p4[(g + u * ry) * C + tx] = make_float4(pp[u].x * be[0] + zz[u].x, pp[u].y * be[1] + zz[u].y,
+                                              pp[u].z * be[2] + zz[u].z, pp[u].w * be[3] + zz[u].w);
+  }
+  for (; g < ngroups; g += ry) {
+    if (g < full) {
+      const int64_t i0 = g * C + tx;
+      const float4 zz = z4[i0], pp = p4[i0];
+      p4[i0] = make_float4(pp.x * be[0] + zz.x, pp.y * be[1] + zz.y, pp.z * be[2] + zz.z, pp.w * be[3] + zz.w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (g * 4 + m.dr[i] < nrows) {
+          const int64_t e = base + (g * 4 + m.dr[i]) * C + m.c[i];
+          pvec[e] = pvec[e] * be[i] + z[e];
+        }
+      }
+    }
+  }
+}
+
 // ---- one CTA: stop test + tridiagonal update (linear_cg.py:302-332) ---------------------------------------
 template <typename T>
 __global__ void k_control(lob_cg_params p, int k, const double* __restrict__ alpha, const double* __restrict__ beta,
@@ -514,6 +711,15 @@ static Launch make_launch(const CgLayout& L) {
   l.d = Dims{L.N, L.C, L.nchunks, L.rows_per_chunk};
   return l;
 }
+
+// the float4 kernels need fp32, one thread per column, and 16-byte addressable batch elements / vectors
+static bool v4_ok(const lob_cg_params* p, const CgLayout& L, std::initializer_list<const void*> ptrs) {
+  if (p->dtype != LOB_F32 || p->C > 128 || L.cx != p->C || ((p->N * p->C) % 4) != 0) return false;
+  for (const void* q : ptrs)
+    if (q && (reinterpret_cast<uintptr_t>(q) & 15) != 0) return false;
+  return true;
+}
+static size_t v4_smem(const CgLayout& L) { return sizeof(double) * L.cx * L.ry * 4 + sizeof(float) * L.cx; }
 
 // long caller-supplied partial lists are folded once into ws (slot 0: <p,Ap>, slot 1: <r,z>)
 static int fold_parts(const CgLayout& L, const CgPtrs& P, const Launch& l, const double*& parts, int& n_parts, int slot,
@@ -632,6 +838,13 @@ extern "C" int lob_cg_step_xr(const lob_cg_params* p, void* ws, int32_t k, const
       parts = P.parts_a;
       nparts = L.nchunks;
     }
+    if (v4_ok(p, L, {ap, pvec, x, r})) {
+      k_step_xr_v4<<<l.grid, l.block, v4_smem(L), st>>>(l.d, (const float*)ap, (const float*)pvec, (float*)x, (float*)r,
+                                                        parts, nparts, P.rz + (size_t)(k & 1) * bc, P.conv, P.alpha,
+                                                        P.parts_rr, P.status, p->eps, k == 0);
+      LOB_TRY(check_launch("k_step_xr_v4"));
+      return LOB_OK;
+    }
     k_step_xr<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, (const scalar_t*)ap, (const scalar_t*)pvec,
                                                          (scalar_t*)x, (scalar_t*)r, parts, nparts,
                                                          P.rz + (size_t)(k & 1) * bc, P.conv, P.alpha, P.parts_rr,
@@ -668,11 +881,19 @@ extern "C" int lob_cg_step_p(const lob_cg_params* p, void* ws, int32_t k, const 
         parts_rz = P.parts_rz;
       }
     }
-    k_step_p<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, zz, (scalar_t*)pvec, parts_rz, n_rz, P.parts_rr,
-                                                        P.rz + (size_t)(k & 1) * bc, P.rz + (size_t)((k + 1) & 1) * bc,
-                                                        P.beta, P.resid, P.conv, P.rhs_zero, P.status, p->eps,
-                                                        p->stop_updating_after);
-    LOB_TRY(check_launch("k_step_p"));
+    if (v4_ok(p, L, {zz, pvec})) {
+      k_step_p_v4<<<l.grid, l.block, v4_smem(L), st>>>(l.d, (const float*)zz, (float*)pvec, parts_rz, n_rz, P.parts_rr,
+                                                       P.rz + (size_t)(k & 1) * bc, P.rz + (size_t)((k + 1) & 1) * bc,
+                                                       P.beta, P.resid, P.conv, P.rhs_zero, P.status, p->eps,
+                                                       p->stop_updating_after);
+      LOB_TRY(check_launch("k_step_p_v4"));
+    } else {
+      k_step_p<scalar_t><<<l.grid, l.block, l.smem, st>>>(l.d, zz, (scalar_t*)pvec, parts_rz, n_rz, P.parts_rr,
+                                                          P.rz + (size_t)(k & 1) * bc,
+                                                          P.rz + (size_t)((k + 1) & 1) * bc, P.beta, P.resid, P.conv,
+                                                          P.rhs_zero, P.status, p->eps, p->stop_updating_after);
+      LOB_TRY(check_launch("k_step_p"));
+    }
     k_control<scalar_t><<<1, 1024, 0, st>>>(*p, k, P.alpha, P.beta, P.resid, P.prev_ar, P.prev_beta,
                                             (scalar_t*)t_mat, P.status);
     LOB_TRY(check_launch("k_control"));

@@ -136,6 +136,23 @@ k_toeplitz_unpad(int64_t N, int64_t C, int64_t L, const T* __restrict__ yt, T sc
 }
 
 
+// Copies `count` consecutive elements global -> shared with 16-byte loads when both sides allow it (every thread of the
+// block takes part; no barrier inside).  Wide loads are what puts enough bytes in flight: with 4-byte loads the
+// write-back passes below ran at 3 TB/s, stalled on the long scoreboard with DRAM a third busy (ncu).
+template <typename T>
+__device__ __forceinline__ void stage_flat(T* __restrict__ dst, const T* __restrict__ src, int count, int tid, int nthr) {
+  constexpr int V = 16 / sizeof(T);
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const int nv = count / V;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int i = tid; i < nv; i += nthr) d4[i] = s4[i];
+    for (int i = nv * V + tid; i < count; i += nthr) dst[i] = src[i];
+  } else {
+    for (int i = tid; i < count; i += nthr) dst[i] = src[i];
+  }
+}
+
 // Flat-coalesced versions of the two transposing passes (used when a row block of all C columns fits in shared memory):
 // a block of `rows` vector rows is ONE contiguous run of rows * C elements in (B, N, C), read / written with
 // consecutive threads on consecutive addresses; the plane side moves `rows` consecutive samples per column.  The
@@ -172,51 +189,78 @@ k_planes_in(int64_t N, int64_t C, int64_t L, int rows, const T* __restrict__ X, 
     for (int l = lane; l < span; l += 32) xb[(int64_t)c * L + n0 + l] = l < valid ? tile[l * ld + c] : (T)0;
 }
 
+// blockDim.x = C * ry threads (ry = 256 / C): in the write phase thread (tx = column, ty) owns the elements
+// (row ty + k ry, column tx) -- consecutive threads still touch consecutive addresses (a row block is one contiguous
+// run), and every thread stays in ONE column, so the optional <X, Y> partial sums are a register accumulation plus one
+// reduction over ty at the end.
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_planes_out(int64_t N, int64_t C, int64_t L, int rows, const T* __restrict__ yt, T scale, const T* __restrict__ X,
              const T* __restrict__ d, int64_t d_bs, int64_t d_st, T* __restrict__ Y, double* __restrict__ dots) {
   extern __shared__ __align__(16) unsigned char pl_smem[];
-  T* tile = reinterpret_cast<T*>(pl_smem);
+  T* tile = reinterpret_cast<T*>(pl_smem);             // [rows][C | 1]  gathered planes
   const int ld = (int)C | 1;
+  T* xs = tile + (rows * ld + 3) / 4 * 4;              // [rows][C]      X rows of this block (same pitch as global)
+  T* ds = xs + (rows * (int)C + 3) / 4 * 4;            // [rows]         diagonal
   const int64_t b = blockIdx.y, n0 = (int64_t)blockIdx.x * rows;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int valid = (int)min((int64_t)rows, N - n0);
   const T* yb = yt + b * C * L;
-  for (int c = warp; c < C; c += 8)
-    for (int l = lane; l < valid; l += 32) tile[l * ld + c] = yb[(int64_t)c * L + n0 + l];
-  __syncthreads();
   const int64_t base = (b * N + n0) * C;
-  const int dq = 256 / (int)C, dr = 256 - dq * (int)C;
-  int r = tid / (int)C, c = tid - r * (int)C;
-  for (int e = tid; e < valid * (int)C; e += 256) {
-    T v = scale * tile[r * ld + c];
-    const T x = (d || dots) ? X[base + e] : (T)0;
-    if (d) v += d[b * d_bs + (n0 + r) * d_st] * x;
-    Y[base + e] = v;
-    if (dots) tile[r * ld + c] = x * v;  // this thread's own element: no hazard
-    r += dq;
-    c += dr;
-    if (c >= (int)C) { c -= (int)C; ++r; }
+  const bool need_x = d || dots;
+  // every global read of the block is requested before the one barrier
+  const int shift = 31 - __clz(rows);  // rows is a power of two (planes_rows)
+  for (int idx = tid; idx < (int)C * rows; idx += nthr) {
+    const int c = idx >> shift, l = idx & (rows - 1);
+    if (l < valid) tile[l * ld + c] = yb[(int64_t)c * L + n0 + l];
+  }
+  if (need_x) stage_flat(xs, X + base, valid * (int)C, tid, nthr);
+  if (d)
+    for (int l = tid; l < valid; l += nthr) ds[l] = d[b * d_bs + (n0 + l) * d_st];
+  __syncthreads();
+  const int ry = nthr / (int)C;
+  const int ty = tid / (int)C, tx = tid - ty * (int)C;
+  double acc = 0.0;
+  for (int r = ty; r < valid; r += ry) {
+    const T x = need_x ? xs[r * (int)C + tx] : (T)0;
+    T v = scale * tile[r * ld + tx];
+    if (d) v += ds[r] * x;
+    Y[base + (int64_t)r * C + tx] = v;
+    acc += (double)x * (double)v;
   }
   if (dots) {
     // partial <X, Y> of this row block per column (linear_cg.py:250-251 fused into the last pass of the product)
     __syncthreads();
-    for (int cc = warp; cc < C; cc += 8) {
+    double* red = reinterpret_cast<double*>(pl_smem);  // [ry][C] <= 2 KB (the launcher sizes the buffer for both uses)
+    red[ty * C + tx] = acc;
+    __syncthreads();
+    if (ty == 0) {
       double a = 0.0;
-      for (int l = lane; l < valid; l += 32) a += (double)tile[l * ld + cc];
-      a = warp_sum(a);
-      if (lane == 0) dots[(b * gridDim.x + blockIdx.x) * C + cc] = a;
+      for (int i = 0; i < ry; ++i) a += red[i * C + tx];
+      dots[(b * gridDim.x + blockIdx.x) * C + tx] = a;
     }
   }
 }
 
-// rows per CTA of the flat kernels: up to 128, a multiple of 32, tile within 48 KB; 0: use the 32 x 32-tile kernels
+// shared memory of k_planes_out / k_toeplitz_unpack for `rows` rows: plane tile + X rows + diagonal (+ column scales)
+static size_t out_tile_bytes(int rows, int64_t C, size_t elem) {
+  return ((size_t)(rows * (C | 1) + 3) / 4 * 4 + (size_t)(rows * C + 3) / 4 * 4 + rows + C) * elem;
+}
+
+// rows per CTA of pack / unpack (the tile also holds the C column scales); 0: too many columns
+static int pair_rows(int64_t C, size_t elem) {
+  if (C > 256) return 0;
+  for (int r = 128; r >= 32; r >>= 1)
+    if (out_tile_bytes(r, C, elem) <= 48 * 1024) return r;
+  return 0;
+}
+
+// rows per CTA of the flat kernels: 128, 64 or 32 (a power of two), tile within 48 KB; 0: use the 32 x 32-tile kernels
 static int planes_rows(int64_t C, size_t elem) {
   if (C > 256) return 0;
-  int64_t r = (int64_t)(48 * 1024) / (((C | 1)) * (int64_t)elem);
-  r = std::min<int64_t>(128, r / 32 * 32);
-  return r >= 32 ? (int)r : 0;
+  for (int r = 128; r >= 32; r >>= 1)
+    if (out_tile_bytes(r, C, elem) <= 48 * 1024) return r;
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -244,7 +288,6 @@ __device__ __forceinline__ double col_scale(unsigned long long mb) {
   return __longlong_as_double((long long)(2046 - e) << 52);
 }
 
-constexpr int TP_ROWS = 64;  // vector rows per CTA in pack / unpack
 
 // maxbits[b, c] = bit pattern of max_n |X[b, n, c]|  (non-negative IEEE values order like unsigned integers; the
 // result of an atomic max does not depend on the order of arrival).  block (cx = min(C, 128), ry), grid (chunks, B)
@@ -282,26 +325,27 @@ __global__ void k_toeplitz_colmax(int64_t N, int64_t C, int64_t rows_per_cta, co
 // zt (B, P, L) complex, P = ceil(C / 2):  zt[b, p, l] = (s_2p X[b, l, 2p], s_2p+1 X[b, l, 2p+1]) for l < N, 0 above
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_toeplitz_pack(int64_t N, int64_t C, int64_t L, const T* __restrict__ X,
+k_toeplitz_pack(int64_t N, int64_t C, int64_t L, int rows_cta, const T* __restrict__ X,
                 const typename PairOf<T>::bits* __restrict__ maxbits, typename PairOf<T>::type* __restrict__ zt) {
   using T2 = typename PairOf<T>::type;
   extern __shared__ __align__(16) unsigned char tp_smem[];
-  T* tile = reinterpret_cast<T*>(tp_smem);  // [TP_ROWS][C | 1]
+  T* tile = reinterpret_cast<T*>(tp_smem);  // [rows_cta][C | 1], rows_cta a power of two (planes_rows)
   const int ld = (int)C | 1;
-  T* sc = tile + TP_ROWS * ld;              // [C]
-  const int64_t b = blockIdx.y, n0 = (int64_t)blockIdx.x * TP_ROWS;
+  T* sc = tile + rows_cta * ld;             // [C]
+  const int shift = 31 - __clz(rows_cta);
+  const int64_t b = blockIdx.y, n0 = (int64_t)blockIdx.x * rows_cta;
   const int P = (int)((C + 1) / 2);
   const int tid = threadIdx.x;
   T2* zb = zt + b * P * L;
   if (n0 >= N) {  // zero padding
-    for (int idx = tid; idx < P * TP_ROWS; idx += 256) {
-      const int pp = idx / TP_ROWS, l = idx - pp * TP_ROWS;
+    for (int idx = tid; idx < P * rows_cta; idx += 256) {
+      const int pp = idx >> shift, l = idx & (rows_cta - 1);
       if (n0 + l < L) zb[(int64_t)pp * L + n0 + l] = T2{(T)0, (T)0};
     }
     return;
   }
   for (int c = tid; c < C; c += 256) sc[c] = col_scale(maxbits[b * C + c]);
-  const int rows = (int)min((int64_t)TP_ROWS, N - n0);
+  const int rows = (int)min((int64_t)rows_cta, N - n0);
   const T* src = X + (b * N + n0) * C;
   {  // the rows of this block are one contiguous run: flat coalesced loads, (row, column) advanced without divisions
     const int dq = 256 / (int)C, dr = 256 - dq * (int)C;
@@ -314,8 +358,8 @@ k_toeplitz_pack(int64_t N, int64_t C, int64_t L, const T* __restrict__ X,
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < P * TP_ROWS; idx += 256) {
-    const int pp = idx / TP_ROWS, l = idx - pp * TP_ROWS;
+  for (int idx = tid; idx < P * rows_cta; idx += 256) {
+    const int pp = idx >> shift, l = idx & (rows_cta - 1);
     if (n0 + l >= L) continue;
     T2 z{(T)0, (T)0};
     if (l < rows) {
@@ -345,54 +389,73 @@ __global__ void k_toeplitz_mulr(int64_t P, int64_t L, const T* __restrict__ fr, 
   zt[e + 1] = c;
 }
 
-// Y[b, n, c] = (scale / s_c) * part_c(zt[b, c / 2, n]) (+ d (.) X)
+// Y[b, n, c] = (scale / s_c) * part_c(zt[b, c / 2, n]) (+ d (.) X); structure of k_planes_out
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_toeplitz_unpack(int64_t N, int64_t C, int64_t L, const typename PairOf<T>::type* __restrict__ zt, T scale,
-                  const typename PairOf<T>::bits* __restrict__ maxbits, const T* __restrict__ X,
+k_toeplitz_unpack(int64_t N, int64_t C, int64_t L, int rows_cta, const typename PairOf<T>::type* __restrict__ zt,
+                  T scale, const typename PairOf<T>::bits* __restrict__ maxbits, const T* __restrict__ X,
                   const T* __restrict__ d, int64_t d_bs, int64_t d_st, T* __restrict__ Y, double* __restrict__ dots) {
   using T2 = typename PairOf<T>::type;
   extern __shared__ __align__(16) unsigned char tp_smem[];
-  T* tile = reinterpret_cast<T*>(tp_smem);
+  T* tile = reinterpret_cast<T*>(tp_smem);                 // [rows][C | 1]
   const int ld = (int)C | 1;
-  T* sc = tile + TP_ROWS * ld;
-  const int64_t b = blockIdx.y, n0 = (int64_t)blockIdx.x * TP_ROWS;
+  T* xs = tile + (rows_cta * ld + 3) / 4 * 4;              // [rows][C]
+  T* ds = xs + (rows_cta * (int)C + 3) / 4 * 4;            // [rows]
+  T* sc = ds + rows_cta;                                   // [C]
+  const int shift = 31 - __clz(rows_cta);
+  const int64_t b = blockIdx.y, n0 = (int64_t)blockIdx.x * rows_cta;
   const int P = (int)((C + 1) / 2);
-  const int tid = threadIdx.x;
-  const int rows = (int)min((int64_t)TP_ROWS, N - n0);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int rows = (int)min((int64_t)rows_cta, N - n0);
+  const int64_t base = (b * N + n0) * C;
+  const bool need_x = d || dots;
   // an all-zero input column gives exactly zero (not its partner's rounding noise)
-  for (int c = tid; c < C; c += 256) sc[c] = maxbits[b * C + c] ? scale / col_scale(maxbits[b * C + c]) : (T)0;
+  for (int c = tid; c < C; c += nthr) sc[c] = maxbits[b * C + c] ? scale / col_scale(maxbits[b * C + c]) : (T)0;
   const T2* zb = zt + b * P * L;
-  for (int idx = tid; idx < P * TP_ROWS; idx += 256) {
-    const int pp = idx / TP_ROWS, l = idx - pp * TP_ROWS;
+  // two samples (32 bytes of fp64, 16 of fp32) per load: L and n0 are even, so the pair is aligned
+  for (int idx = tid; idx < P * (rows_cta >> 1); idx += nthr) {
+    const int pp = idx >> (shift - 1), l = (idx & ((rows_cta >> 1) - 1)) << 1;
     if (l < rows) {
-      const T2 z = zb[(int64_t)pp * L + n0 + l];
-      tile[l * ld + 2 * pp] = z.x;
-      if (2 * pp + 1 < C) tile[l * ld + 2 * pp + 1] = z.y;
+      const T2* zp = zb + (int64_t)pp * L + n0 + l;
+      T2 z0, z1;
+      if constexpr (sizeof(T) == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(zp);
+        z0 = T2{q.x, q.y}, z1 = T2{q.z, q.w};
+      } else {
+        z0 = zp[0], z1 = zp[1];
+      }
+      tile[l * ld + 2 * pp] = z0.x;
+      if (2 * pp + 1 < C) tile[l * ld + 2 * pp + 1] = z0.y;
+      if (l + 1 < rows) {
+        tile[(l + 1) * ld + 2 * pp] = z1.x;
+        if (2 * pp + 1 < C) tile[(l + 1) * ld + 2 * pp + 1] = z1.y;
+      }
     }
   }
+  if (need_x) stage_flat(xs, X + base, rows * (int)C, tid, nthr);
+  if (d)
+    for (int l = tid; l < rows; l += nthr) ds[l] = d[b * d_bs + (n0 + l) * d_st];
   __syncthreads();
-  const int64_t base = (b * N + n0) * C;
-  const int dq = 256 / (int)C, dr = 256 - dq * (int)C;
-  int r = tid / (int)C, c = tid - r * (int)C;
-  for (int e = tid; e < rows * (int)C; e += 256) {
-    T v = tile[r * ld + c] * sc[c];
-    const T x = (d || dots) ? X[base + e] : (T)0;
-    if (d) v += d[b * d_bs + (n0 + r) * d_st] * x;
-    Y[base + e] = v;
-    if (dots) tile[r * ld + c] = x * v;
-    r += dq;
-    c += dr;
-    if (c >= (int)C) { c -= (int)C; ++r; }
+  const int ry = nthr / (int)C;
+  const int ty = tid / (int)C, tx = tid - ty * (int)C;
+  const T scl = sc[tx];
+  double acc = 0.0;
+  for (int r = ty; r < rows; r += ry) {
+    const T x = need_x ? xs[r * (int)C + tx] : (T)0;
+    T v = tile[r * ld + tx] * scl;
+    if (d) v += ds[r] * x;
+    Y[base + (int64_t)r * C + tx] = v;
+    acc += (double)x * (double)v;
   }
   if (dots) {
     __syncthreads();
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int cc = warp; cc < C; cc += 8) {
+    double* red = reinterpret_cast<double*>(tp_smem);  // [ry][C] <= 2 KB
+    red[ty * C + tx] = acc;
+    __syncthreads();
+    if (ty == 0) {
       double a = 0.0;
-      for (int l = lane; l < rows; l += 32) a += (double)tile[l * ld + cc];
-      a = warp_sum(a);
-      if (lane == 0) dots[(b * gridDim.x + blockIdx.x) * C + cc] = a;
+      for (int i = 0; i < ry; ++i) a += red[i * C + tx];
+      dots[(b * gridDim.x + blockIdx.x) * C + tx] = a;
     }
   }
 }
@@ -565,12 +628,13 @@ extern "C" int lob_toeplitz_pack(int32_t dtype, int64_t B, int64_t N, int64_t C,
   LOB_REQUIRE(B > 0 && N > 0 && C > 0 && L >= N, "lob_toeplitz_pack: bad sizes");
   LOB_REQUIRE(B <= 65535 && C <= 4096, "lob_toeplitz_pack: flattened batch > 65535 or more than 4096 columns not supported");
   LOB_REQUIRE(X && maxbits && zt, "lob_toeplitz_pack: NULL pointer");
-  dim3 grid((unsigned)cdiv(L, TP_ROWS), (unsigned)B);
   LOB_DISPATCH_DTYPE(dtype, {
-    const size_t smem = sizeof(scalar_t) * ((size_t)TP_ROWS * ((int)C | 1) + C);
-    LOB_REQUIRE(smem <= 48 * 1024, "lob_toeplitz_pack: too many columns for one shared-memory tile");
+    const int rows = pair_rows(C, sizeof(scalar_t));
+    LOB_REQUIRE(rows > 0, "lob_toeplitz_pack: too many columns for one shared-memory tile (split the column block)");
+    dim3 grid((unsigned)cdiv(L, rows), (unsigned)B);
+    const size_t smem = sizeof(scalar_t) * ((size_t)rows * ((int)C | 1) + C);
     k_toeplitz_pack<scalar_t><<<grid, 256, smem, (cudaStream_t)stream>>>(
-        N, C, L, (const scalar_t*)X, (const typename PairOf<scalar_t>::bits*)maxbits,
+        N, C, L, rows, (const scalar_t*)X, (const typename PairOf<scalar_t>::bits*)maxbits,
         (typename PairOf<scalar_t>::type*)zt);
     return check_launch("k_toeplitz_pack");
   });
@@ -588,7 +652,10 @@ extern "C" int lob_toeplitz_mulr(int32_t dtype, int64_t B, int64_t P, int64_t L,
   });
 }
 
-extern "C" int32_t lob_toeplitz_unpack_parts(int64_t N) { return (int32_t)cdiv(N, TP_ROWS); }
+extern "C" int32_t lob_toeplitz_unpack_parts(int32_t dtype, int64_t N, int64_t C) {
+  const int rows = pair_rows(C, dsize(dtype));
+  return rows ? (int32_t)cdiv(N, rows) : 0;
+}
 
 extern "C" int lob_toeplitz_unpack(int32_t dtype, int64_t B, int64_t N, int64_t C, int64_t L, const void* zt,
                                    double scale, const void* maxbits, const void* X, const void* d,
@@ -596,12 +663,15 @@ extern "C" int lob_toeplitz_unpack(int32_t dtype, int64_t B, int64_t N, int64_t 
   LOB_REQUIRE(B > 0 && N > 0 && C > 0 && L >= N, "lob_toeplitz_unpack: bad sizes");
   LOB_REQUIRE(B <= 65535 && C <= 4096, "lob_toeplitz_unpack: flattened batch > 65535 or more than 4096 columns not supported");
   LOB_REQUIRE(zt && maxbits && Y && ((!d && !dots) || X), "lob_toeplitz_unpack: NULL pointer");
-  dim3 grid((unsigned)cdiv(N, TP_ROWS), (unsigned)B);
   LOB_DISPATCH_DTYPE(dtype, {
-    const size_t smem = sizeof(scalar_t) * ((size_t)TP_ROWS * ((int)C | 1) + C);
-    LOB_REQUIRE(smem <= 48 * 1024, "lob_toeplitz_unpack: too many columns for one shared-memory tile");
-    k_toeplitz_unpack<scalar_t><<<grid, 256, smem, (cudaStream_t)stream>>>(
-        N, C, L, (const typename PairOf<scalar_t>::type*)zt, (scalar_t)scale,
+    const int rows = pair_rows(C, sizeof(scalar_t));
+    LOB_REQUIRE(rows > 0, "lob_toeplitz_unpack: too many columns for one shared-memory tile (split the column block)");
+    dim3 grid((unsigned)cdiv(N, rows), (unsigned)B);
+    const size_t smem = out_tile_bytes(rows, C, sizeof(scalar_t));
+    const int ry = std::max<int>(1, 256 / (int)C);
+    k_toeplitz_unpack<scalar_t><<<grid, (unsigned)(ry * C), std::max(smem, sizeof(double) * ry * (size_t)C),
+                                  (cudaStream_t)stream>>>(
+        N, C, L, rows, (const typename PairOf<scalar_t>::type*)zt, (scalar_t)scale,
         (const typename PairOf<scalar_t>::bits*)maxbits, (const scalar_t*)X, (const scalar_t*)d, d_batch_stride,
         d_stride, (scalar_t*)Y, dots);
     return check_launch("k_toeplitz_unpack");
@@ -625,8 +695,10 @@ extern "C" int lob_toeplitz_unpad(int32_t dtype, int64_t B, int64_t N, int64_t C
   LOB_DISPATCH_DTYPE(dtype, {
     const int rows = planes_rows(C, sizeof(scalar_t));
     if (rows) {
-      const size_t smem = sizeof(scalar_t) * (size_t)rows * ((int)C | 1);
-      k_planes_out<scalar_t><<<dim3((unsigned)cdiv(N, rows), (unsigned)B), 256, smem, (cudaStream_t)stream>>>(
+      const int ry = std::max<int>(1, 256 / (int)C);
+      const size_t smem = std::max(out_tile_bytes(rows, C, sizeof(scalar_t)), sizeof(double) * ry * (size_t)C);
+      k_planes_out<scalar_t><<<dim3((unsigned)cdiv(N, rows), (unsigned)B), (unsigned)(ry * C), smem,
+                               (cudaStream_t)stream>>>(
           N, C, L, rows, (const scalar_t*)yt, (scalar_t)scale, (const scalar_t*)X, (const scalar_t*)d, d_batch_stride,
           d_stride, (scalar_t*)Y, dots);
       return check_launch("k_planes_out");

@@ -280,6 +280,18 @@ def test_structured_products_fused_dot_partials():
     check(npy(dots.sum(1)), npy((Xd * Yd).sum(-2)), 1e-13)
 
 
+def test_toeplitz_matmul_wide_column_blocks():
+    """Column counts beyond the 33 of the solver: 100 columns take 64-row tiles in pack / unpack, 300 columns (more than
+    one shared-memory tile holds) are split into column blocks on the host."""
+    gen = torch.Generator(device=DEV).manual_seed(19)
+    N = 700
+    col = torch.exp(-0.5 * (torch.arange(N, device=DEV, dtype=torch.float64) / 6.0) ** 2)
+    for C in (100, 300):
+        X = torch.randn(N, C, device=DEV, dtype=torch.float64, generator=gen)
+        y = ToeplitzLinearOperator(col)._matmul(X)
+        check(npy(y), ko.sym_toeplitz_matmul(npy(col), npy(X)), 1e-12)
+
+
 def test_cfg4_toeplitz_baseline_shape_vs_oracle():
     """BASELINE configs[3]: toeplitz_matmul at N = 2^20 with the full 33-column block, one batch element, fp32, against
     the oracle's length-(2N-1) complex-FFT restatement (utils/toeplitz.py:131-149)."""

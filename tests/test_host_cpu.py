@@ -74,7 +74,8 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert b"NULL" in lib.lob_last_error()
     assert lib.lob_toeplitz_mulr(0, 1, 2, 15, None, 0, None, None) == -1  # odd transform length
     assert lib.lob_toeplitz_unpack(0, 1, 8, 3, 16, None, 1.0, None, None, None, 0, 0, None, None, None) == -1
-    assert lib.lob_toeplitz_unpack_parts(1000) == 16 and lib.lob_toeplitz_unpad_parts(0, 1000, 33) == 8
+    assert lib.lob_toeplitz_unpack_parts(0, 1000, 33) == 8 and lib.lob_toeplitz_unpad_parts(0, 1000, 33) == 8
+    assert lib.lob_toeplitz_unpack_parts(0, 1000, 100) == 32 and lib.lob_toeplitz_unpack_parts(1, 1000, 300) == 0
 
 
 def test_lanczos_host_checks_and_no_cpu_fallback():
