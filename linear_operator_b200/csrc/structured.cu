@@ -210,9 +210,23 @@ k_planes_out(int64_t N, int64_t C, int64_t L, int rows, const T* __restrict__ yt
   const bool need_x = d || dots;
   // every global read of the block is requested before the one barrier
   const int shift = 31 - __clz(rows);  // rows is a power of two (planes_rows)
-  for (int idx = tid; idx < (int)C * rows; idx += nthr) {
-    const int c = idx >> shift, l = idx & (rows - 1);
-    if (l < valid) tile[l * ld + c] = yb[(int64_t)c * L + n0 + l];
+  if (sizeof(T) == 4 && (L & 3) == 0 && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(yt) & 15) == 0) {
+    // four consecutive samples of a plane per load (n0 and L are multiples of 4: aligned)
+    for (int idx = tid; idx < (int)C * (rows >> 2); idx += nthr) {
+      const int c = idx >> (shift - 2), l = (idx & ((rows >> 2) - 1)) << 2;
+      if (l < valid) {
+        const float4 q = *reinterpret_cast<const float4*>(yb + (int64_t)c * L + n0 + l);
+        const T v[4] = {(T)q.x, (T)q.y, (T)q.z, (T)q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (l + i < valid) tile[(l + i) * ld + c] = v[i];
+      }
+    }
+  } else {
+    for (int idx = tid; idx < (int)C * rows; idx += nthr) {
+      const int c = idx >> shift, l = idx & (rows - 1);
+      if (l < valid) tile[l * ld + c] = yb[(int64_t)c * L + n0 + l];
+    }
   }
   if (need_x) stage_flat(xs, X + base, valid * (int)C, tid, nthr);
   if (d)
