@@ -331,13 +331,30 @@ constexpr int SPLITP_KT = 64;
 
 __global__ void __launch_bounds__(256)
 k_split_x2p(const float* __restrict__ X, float* __restrict__ Xs, int64_t K, int64_t Kp, int C, int H) {
-  extern __shared__ float xsp[];  // [SPLITP_KT][C | 1]
+  extern __shared__ __align__(16) float xsp[];  // [SPLITP_KT][C | 1]
   const int ldx = C | 1;
   const int64_t b = blockIdx.y;
   const int64_t k0 = (int64_t)blockIdx.x * SPLITP_KT;
   const int kvalid = (int)max((int64_t)0, min((int64_t)SPLITP_KT, K - k0));
   const float* src = X + (b * K + k0) * C;
-  for (int e = threadIdx.x; e < kvalid * C; e += blockDim.x) xsp[(e / C) * ldx + (e % C)] = src[e];
+  // the 64 x C block is one contiguous run: 16-byte loads when the pitch needs no padding (odd C) and the run is
+  // 16-byte addressable, else element-wise with (row, column) advanced without divisions
+  if (ldx == C && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int nv = (kvalid * C) >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(xsp);
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) d4[i] = s4[i];
+    for (int i = (nv << 2) + threadIdx.x; i < kvalid * C; i += blockDim.x) xsp[i] = src[i];
+  } else {
+    const int dq = blockDim.x / C, dr = blockDim.x - dq * C;
+    int r = threadIdx.x / C, c = threadIdx.x - r * C;
+    for (int e = threadIdx.x; e < kvalid * C; e += blockDim.x) {
+      xsp[r * ldx + c] = src[e];
+      r += dq;
+      c += dr;
+      if (c >= C) { c -= C; ++r; }
+    }
+  }
   __syncthreads();
   // each thread writes one 16-byte word (4 consecutive k of one operand row): 16 lanes cover the 64 k of a row
   const int q4 = threadIdx.x & 15;
