@@ -10,6 +10,8 @@
 //                                    the arg-max / error candidates of the next step.
 // Index semantics reproduced exactly: candidates are compared in *permuted order* (first maximal position wins, like
 // torch.max on the gathered diagonal, :61-63), the swap is the reference's (:67-70), perm is int64.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace lob {
@@ -28,11 +30,29 @@ struct PcLayout {
 
 static PcLayout pc_layout(int64_t B, int64_t N, int rank, size_t es) {
   PcLayout L;
-  int64_t nch = cdiv((int64_t)kNumSMs * 4, B);
+  // Column chunks per batch element.  Small batches: enough CTAs for ~4 per SM (under one wave whatever the row
+  // functor's register count).  Large batches, where one chunk per element already overfills the GPU (B = 1024,
+  // N = 5000 ran 1.15 waves of 6 CTAs per SM -- the second 15 % full): the count that maximises (fill of the last
+  // wave) x (threads of a 256-thread CTA that own a 16-byte column group).
   int64_t maxch = cdiv(N, 256);
+  if (maxch > 256) maxch = 256;
+  if (maxch < 1) maxch = 1;
+  int64_t nch = cdiv((int64_t)kNumSMs * 4, B);
   if (nch > maxch) nch = maxch;
-  if (nch > 256) nch = 256;
   if (nch < 1) nch = 1;
+  if (B >= (int64_t)kNumSMs * 4) {
+    const double slots = (double)kNumSMs * 6;
+    double best = -1.0;
+    for (int64_t c = 1; c <= maxch && c <= 16; ++c) {
+      const int64_t cols = cdiv(cdiv(N, c), 4) * 4, groups = cols / 4;
+      const double waves = (double)(B * cdiv(N, cols)) / slots;
+      const double eff = (waves / ceil(waves)) * ((double)groups / (double)(cdiv(groups, 256) * 256));
+      if (eff > best + 1e-9) {
+        best = eff;
+        nch = c;
+      }
+    }
+  }
   L.cols_per_chunk = cdiv(cdiv(N, nch), 4) * 4;  // multiple of 4: lets the fp32 update use 16-byte words
   L.nchunks = (int)cdiv(N, L.cols_per_chunk);
   size_t o = 0;
@@ -353,6 +373,19 @@ k_pc_update_v4(Src src, int64_t N, int rankmax, int m, int nchunks, int64_t cpc,
     if (pp[0] <= m && pp[1] <= m && pp[2] <= m && pp[3] <= m) continue;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     int t = 0;
+    for (; t + 7 < m; t += 8) {  // eight rows of L requested before the first is used (same order of the additions)
+      float4 l[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) l[q] = *reinterpret_cast<const float4*>(Lb + (int64_t)(t + q) * N + i);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float uq = u[t + q];
+        s[0] = __fadd_rn(s[0], __fmul_rn(uq, l[q].x));
+        s[1] = __fadd_rn(s[1], __fmul_rn(uq, l[q].y));
+        s[2] = __fadd_rn(s[2], __fmul_rn(uq, l[q].z));
+        s[3] = __fadd_rn(s[3], __fmul_rn(uq, l[q].w));
+      }
+    }
     for (; t + 3 < m; t += 4) {
       float4 l[4];
 #pragma unroll
