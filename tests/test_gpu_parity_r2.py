@@ -292,6 +292,25 @@ def test_toeplitz_matmul_wide_column_blocks():
         check(npy(y), ko.sym_toeplitz_matmul(npy(col), npy(X)), 1e-12)
 
 
+@pytest.mark.parametrize("N,C", [(1001, 4), (1003, 8), (999, 12), (1000, 33), (1002, 2), (1001, 3)])
+def test_linear_cg_float4_vector_kernels_ragged_shapes(N, C):
+    """fp32 mBCG through the float4 forms of the per-iteration vector kernels (N * C % 4 == 0): row counts that leave a
+    ragged last group of four rows, column counts around the lane width, against the oracle's restatement of the
+    reference on identical inputs (same iteration count, tridiagonals included); the last shape (N * C odd) takes the
+    scalar kernels."""
+    from linear_operator_b200.utils import linear_cg
+
+    gen = torch.Generator(device=DEV).manual_seed(100 + N + C)
+    W = torch.randn(2, N, N, device=DEV, generator=gen)  # full-rank spectrum in [0.5, 4.5]: no early breakdown of the
+    A = W @ W.mT / N + 0.5 * torch.eye(N, device=DEV)    # Lanczos coefficients, which would amplify fp32 rounding
+    rhs = torch.randn(2, N, C, device=DEV, generator=gen)
+    nt = min(C, 2)
+    x, t = linear_cg(A, rhs, n_tridiag=nt, max_iter=12, max_tridiag_iter=8, tolerance=1e-9)
+    xo, to = ko.linear_cg(npy(A), npy(rhs), n_tridiag=nt, max_iter=12, max_tridiag_iter=8, tolerance=1e-9)
+    check(npy(x), xo, F32_RTOL)
+    check(npy(t), to, F32_RTOL)
+
+
 def test_cfg4_toeplitz_baseline_shape_vs_oracle():
     """BASELINE configs[3]: toeplitz_matmul at N = 2^20 with the full 33-column block, one batch element, fp32, against
     the oracle's length-(2N-1) complex-FFT restatement (utils/toeplitz.py:131-149)."""
