@@ -19,7 +19,14 @@
 //   lo MMA  (A_lo from TMEM, N = 2 h: the first h rows of either CTA's half):
 //                                               D[:, 0:h]  += A_lo X_hi[0:h]     D[:, h:2h] += A_lo X_hi[h:2h]
 //   y[:, c] = D[:, c] + D[:, 3h + c]  (c < h),   y[:, c] = D[:, c] + D[:, h + c]  (c >= h)        (3xTF32)
-// TMEM per CTA (512 columns): 4 accumulators x 4 h columns (2 M tiles x 2 buffers) + A_lo operand slots of 2 BK columns.
+// Column counts just above a multiple of 16 (C = 2 g + e, g % 8 == 0, 1 <= e <= 4: the solver's 32 probes + 1 right-hand
+// side) take a tighter layout: 2 g + 8 rows per CTA instead of 2 h = 2 (g + 8),
+//   [ X_hi[0:g] ; extras (8 rows: x_hi, x_lo of column 2g + j at rows 2j, 2j + 1, zeros) ; X_lo[g:2g] |
+//     X_hi[g:2g] ; zeros (8) ; X_lo[0:g] ]
+// hi MMA N = 4 g + 16 (80 instead of 96 at C = 33), lo MMA N = 2 g + 16 over the first g + 8 rows of either half: it
+// adds A_lo x_hi (and a harmless A_lo x_lo) to the extras' own columns and A_lo 0 to the columns behind CTA 1's hi rows.
+//   y[:, c] = D[c] + D[3g+16+c] (c < g),  D[c+8] + D[c+8+g] (g <= c < 2g),  D[g+2j] + D[g+2j+1] (c = 2g + j)
+// TMEM per CTA (512 columns): 4 accumulators x N_hi columns (2 M tiles x 2 buffers) + A_lo operand slots of 2 BK columns.
 // Synchronisation: TMA -> converters and MMA commit -> TMA / converters / epilogue are CTA-local barriers (the commits
 // are multicast to both CTAs); converters -> MMA and epilogue -> MMA arrive on the LEADER's barriers from both CTAs.
 // Warp roles (512 threads per CTA): 0 TMA producer, 1 MMA issuer (leader CTA only), 2 TMEM allocator, 4-7 epilogue,
@@ -47,8 +54,10 @@ struct P2Params {
   double* dots;
   int64_t M, K, C;
   int n_parts;
-  int H;         // half width h (multiple of 8)
-  int xbytes;    // bytes of one CTA's X tile (2 h x BK x 4, rounded up to 1 KB)
+  int G;         // half width g of the regular columns (multiple of 8): columns [0, 2 g)
+  int MX;        // 0, or 8: extras block (columns [2 g, C), at most 4) in the middle of CTA 0's tile
+  int R;         // rows of one CTA's X tile: 2 g + MX
+  int xbytes;    // bytes of one CTA's X tile (R x BK x 4, rounded up to 1 KB)
   int SA;        // ring stages
   int MTP;       // pair tiles (512 rows) per batch element
   int64_t nptiles;
@@ -88,7 +97,7 @@ k_dense_stream2p(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t rank = cluster_ctarank();
   const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int nkb = (int)((p.K + BK - 1) / BK);
-  const int H = p.H;
+  const int G = p.G, MX = p.MX;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -125,7 +134,7 @@ k_dense_stream2p(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t xtx = (uint32_t)(2 * H * BK * 4);
+      const uint32_t xtx = (uint32_t)(p.R * BK * 4);
       for (int64_t pt = pair; pt < p.nptiles; pt += npairs) {
         const int b = (int)(pt / p.MTP);
         const int m0 = ((int)(pt - (int64_t)b * p.MTP) * 2 + (int)rank) * P2_ROWS;
@@ -134,7 +143,7 @@ k_dense_stream2p(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t dst = smem_u32(sRing + s * stage_bytes);
           const uint32_t bar = smem_u32(&full[s]);
           mbar_arrive_expect_tx(bar, (uint32_t)A_STAGE + xtx);
-          tma_load_3d(dst + A_STAGE, &tmX, bar, kb * BK, (int)rank * 2 * H, b, pol_keep);
+          tma_load_3d(dst + A_STAGE, &tmX, bar, kb * BK, (int)rank * p.R, b, pol_keep);
           tma_load_3d(dst, &tmA, bar, kb * BK, m0, p.a_shared ? 0 : b, pol_stream);
           if (++s == p.SA) { s = 0; ph ^= 1; }
         }
@@ -208,21 +217,27 @@ k_dense_stream2p(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const float dv = (p.dg && rok) ? __ldg(p.dg + b * p.d_bs + row * p.d_st) : 0.f;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + t) * p.acc_stride;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 2 * H; c0 += 16) {
+        for (int c0 = 0; c0 < 2 * G + 2 * MX; c0 += 16) {
           float e[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) e[i] = (need_e && rok && c0 + i < C) ? __ldg(Eb + row * C + c0 + i) : 0.f;
-          // two 8-column groups (H % 8 == 0: a group never straddles the halves); partner columns per the layout above
           uint32_t hi[16], lo[16];
-          const int ca = c0, cb = c0 + 8;
-          DS_LD8(taddr + ca, hi);
-          DS_LD8(taddr + (ca < H ? 3 * H + ca : H + ca), lo);
-          if (cb < 2 * H) {
-            DS_LD8(taddr + cb, (hi + 8));
-            DS_LD8(taddr + (cb < H ? 3 * H + cb : H + cb), (lo + 8));
+          if (c0 < 2 * G) {
+            // two 8-column groups (G % 8 == 0: a group never straddles the halves); partner columns per the layout above
+            const int ca = c0, cb = c0 + 8;
+            DS_LD8(taddr + (ca < G ? ca : ca + MX), hi);
+            DS_LD8(taddr + (ca < G ? 3 * G + 2 * MX + ca : ca + MX + G), lo);
+            DS_LD8(taddr + (cb < G ? cb : cb + MX), (hi + 8));
+            DS_LD8(taddr + (cb < G ? 3 * G + 2 * MX + cb : cb + MX + G), (lo + 8));
           } else {
+            // the extras: column 2 g + j sits at D[g + 2 j] (A_hi x_hi + A_lo x_hi) and D[g + 2 j + 1] (A_hi x_lo)
+            uint32_t v[8];
+            DS_LD8(taddr + G, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int i = 8; i < 16; ++i) hi[i] = lo[i] = 0u;
+            for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hi[i] = v[2 * i], lo[i] = v[2 * i + 1];
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           double pd[16];
@@ -330,7 +345,7 @@ k_dense_stream2p(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 constexpr int SPLITP_KT = 64;
 
 __global__ void __launch_bounds__(256)
-k_split_x2p(const float* __restrict__ X, float* __restrict__ Xs, int64_t K, int64_t Kp, int C, int H) {
+k_split_x2p(const float* __restrict__ X, float* __restrict__ Xs, int64_t K, int64_t Kp, int C, int G, int MX) {
   extern __shared__ __align__(16) float xsp[];  // [SPLITP_KT][C | 1]
   const int ldx = C | 1;
   const int64_t b = blockIdx.y;
@@ -359,11 +374,18 @@ k_split_x2p(const float* __restrict__ X, float* __restrict__ Xs, int64_t K, int6
   // each thread writes one 16-byte word (4 consecutive k of one operand row): 16 lanes cover the 64 k of a row
   const int q4 = threadIdx.x & 15;
   const int kw = (int)min((int64_t)SPLITP_KT, Kp - k0);
-  const int R = 4 * H;
+  const int RT = 2 * G + MX, R = 2 * RT;  // rows of one CTA's tile, of both
   for (int r = threadIdx.x >> 4; r < R; r += blockDim.x >> 4) {
-    const int quarter = r / H, j = r - quarter * H;
-    const int part = quarter & 1;                                 // 0: hi rows, 1: lo rows
-    const int c = (quarter == 0 || quarter == 3) ? j : H + j;
+    const int cta = r >= RT, j = r - cta * RT;
+    int part, c;  // 0: hi rows, 1: lo rows; c >= C: zero row
+    if (j < G) {
+      part = 0, c = cta * G + j;
+    } else if (j < G + MX) {
+      const int jj = j - G;
+      part = jj & 1, c = cta ? C : 2 * G + (jj >> 1);  // extras live in CTA 0's tile only
+    } else {
+      part = 1, c = (1 - cta) * G + (j - G - MX);
+    }
     float o[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < C) {
 #pragma unroll
@@ -425,12 +447,21 @@ static P2Config p2_default_config() {
 constexpr size_t P2_SMEM_MAX = 232448;
 constexpr size_t P2_SMEM_FIXED = 1024 /*alignment*/ + P2_RED_DOUBLES * 8 + 512 /*barriers*/;
 
-static int p2_half_width(int64_t C) { return (int)(((C + 1) / 2 + 7) / 8 * 8); }
+// column layout: regular half width g and extras block (0 or 8 rows); rows of one CTA's operand tile = 2 g + mx
+struct P2Layout {
+  int g, mx;
+  int rows() const { return 2 * g + mx; }
+};
+static P2Layout p2_layout(int64_t C) {
+  const int gl = (int)((C - 1) / 16 * 8);  // largest g (multiple of 8) with 2 g < C
+  if (gl >= 8 && C - 2 * gl <= 4) return {gl, 8};
+  return {(int)(((C + 1) / 2 + 7) / 8 * 8), 0};
+}
 
 size_t dense_stream2p_workspace_bytes(int64_t B, int64_t K, int64_t C) {
   if (B <= 0 || K <= 0 || C <= 0 || C > 48) return 0;
   const int64_t Kp = (K + 3) / 4 * 4;
-  return (size_t)B * 4 * p2_half_width(C) * Kp * sizeof(float);
+  return (size_t)B * 2 * p2_layout(C).rows() * Kp * sizeof(float);
 }
 
 // returns LOB_ERR_UNSUPPORTED when the shape does not qualify (caller falls back to dense_stream2.cu)
@@ -447,7 +478,8 @@ int dense_matmul_stream2p_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, co
   PFN_encodeTiled_p2 enc = p2_encode_fn();
   if (!enc) return LOB_ERR_UNSUPPORTED;
   const int BK = (cfg.bk == 16) ? 16 : 32;
-  const int H = p2_half_width(C);
+  const P2Layout lay = p2_layout(C);
+  const int R = lay.rows();
   const int64_t Kp = (K + 3) / 4 * 4;
   const bool shared = (a_bs == 0);
   const CUtensorMapSwizzle swz = (BK == 32) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -464,9 +496,9 @@ int dense_matmul_stream2p_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, co
     if (r != CUDA_SUCCESS) return LOB_ERR_UNSUPPORTED;
   }
   {
-    cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)(4 * H), (cuuint64_t)B};
-    cuuint64_t gstr[2] = {(cuuint64_t)Kp * 4, (cuuint64_t)(4 * H) * Kp * 4};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(2 * H), 1};
+    cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)(2 * R), (cuuint64_t)B};
+    cuuint64_t gstr[2] = {(cuuint64_t)Kp * 4, (cuuint64_t)(2 * R) * Kp * 4};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)R, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ws, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -475,7 +507,7 @@ int dense_matmul_stream2p_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, co
   }
 
   const int a_stage = P2_ROWS * BK * 4;
-  const int xbytes = (int)align_up((size_t)2 * H * BK * 4, 1024);
+  const int xbytes = (int)align_up((size_t)R * BK * 4, 1024);
   const int stage = a_stage + xbytes;
   int sa = cfg.sa > 0 ? cfg.sa : (int)((P2_SMEM_MAX - P2_SMEM_FIXED) / stage);
   if (sa > P2_MAX_ST) sa = P2_MAX_ST;
@@ -496,17 +528,19 @@ int dense_matmul_stream2p_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, co
   p.K = K;
   p.C = C;
   p.n_parts = (int)cdiv(M, 128);
-  p.H = H;
+  p.G = lay.g;
+  p.MX = lay.mx;
+  p.R = R;
   p.xbytes = xbytes;
   p.SA = sa;
   p.MTP = (int)cdiv(M, 2 * P2_ROWS);
   p.nptiles = B * p.MTP;
   p.a_shared = shared ? 1 : 0;
-  p.idesc_hi = ds::make_idesc_tf32(256, 4 * H);
-  p.idesc_lo = ds::make_idesc_tf32(256, 2 * H);
+  p.idesc_hi = ds::make_idesc_tf32(256, 2 * R);                  // either CTA supplies its R rows
+  p.idesc_lo = ds::make_idesc_tf32(256, 2 * (lay.g + lay.mx));   // ... resp. its first g + mx rows
   p.dbg = cfg.dbg;
   p.acc_bufs = (cfg.acc_bufs == 1) ? 1 : 2;
-  p.acc_stride = 4 * H;
+  p.acc_stride = 2 * R;
   p.slot_base = 2 * p.acc_bufs * p.acc_stride;
   p.nslot = (512 - p.slot_base) / (2 * BK);
   if (p.nslot > 8) p.nslot = 8;
@@ -515,7 +549,7 @@ int dense_matmul_stream2p_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, co
   {
     dim3 grid((unsigned)cdiv(Kp, SPLITP_KT), (unsigned)B);
     const size_t sm = (size_t)SPLITP_KT * ((int)C | 1) * sizeof(float);
-    k_split_x2p<<<grid, 256, sm, st>>>(X, (float*)ws, K, Kp, (int)C, H);
+    k_split_x2p<<<grid, 256, sm, st>>>(X, (float*)ws, K, Kp, (int)C, lay.g, lay.mx);
     LOB_TRY(check_launch("k_split_x2p"));
   }
 

@@ -63,7 +63,7 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert b"NULL" in lib.lob_last_error()
     assert lib.lob_lanczos_init(0, 0, 8, 1, None, None, None) == -1
     # streaming matmul scratch: (B, 2 * round_up(C, 8), K) floats for fp32, none for fp64 or C > 64
-    assert lib.lob_dense_matmul_workspace_bytes(0, 1024, 5000, 5000, 33) == 1024 * 96 * 5000 * 4  # pair kernel: 4 h rows, h = 24
+    assert lib.lob_dense_matmul_workspace_bytes(0, 1024, 5000, 5000, 33) == 1024 * 80 * 5000 * 4  # pair kernel: 2 x (2 g + 8) rows, g = 16
     assert lib.lob_dense_matmul_workspace_bytes(1, 1024, 5000, 5000, 33) == 0
     assert lib.lob_dense_matmul_workspace_bytes(0, 2, 100, 100, 65) == 0
     # Toeplitz column-pair path: sizes and NULL pointers are rejected before anything is launched
