@@ -38,7 +38,8 @@ def _case(B, N, C, with_diag, seed):
 @pytest.mark.parametrize(
     "B,N,C,with_diag",
     [(2, 384, 33, True), (1, 260, 1, False), (2, 1000, 17, True), (2, 512, 48, True), (3, 2052, 33, True),
-     (1, 128, 8, False), (2, 5000, 33, True), (2, 776, 64, True), (40, 300, 33, True)],
+     (1, 128, 8, False), (2, 5000, 33, True), (2, 776, 64, True), (40, 300, 33, True), (2, 640, 36, True),
+     (1, 300, 18, True), (2, 600, 35, False)],
 )
 def test_dense_tc_matches_fp64(B, N, C, with_diag, impl):
     A, X, d, ref = _case(B, N, C, with_diag, 100 + N + C)
