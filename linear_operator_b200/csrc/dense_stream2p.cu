@@ -67,6 +67,8 @@ struct P2Params {
   int slot_base;   // first A_lo operand slot column
   int nslot;       // A_lo operand slots (each 2 * BK columns)
   int acc_bufs;
+  int seg;         // k blocks per accumulator segment (see "segments" in the kernel); >= number of k blocks: one segment
+  int ysum_ld;     // leading dimension (floats) of the running-sum tile in shared memory, 0 when there is one segment
   int dbg;         // harness experiments (LOB_DIAG builds): 1 skip lo MMA, 2 skip conversion, 4 skip all MMAs
 };
 
@@ -83,7 +85,13 @@ k_dense_stream2p(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = A_STAGE + p.xbytes;
   unsigned char* sRing = smem;
-  double* dred = reinterpret_cast<double*>(smem + p.SA * stage_bytes);
+  // Segments.  The tensor core truncates when it adds into its fp32 accumulator: a bias that grows with the number of
+  // k steps (1.5e-8 per contraction index on all-positive data).  Long contractions are therefore cut into segments of
+  // p.seg k blocks that alternate between the two TMEM accumulator buffers; the epilogue warps drain a finished segment
+  // into a running sum in shared memory (round-to-nearest adds) while the MMAs of the next one run, and only the last
+  // segment goes through the output epilogue.  The bias no longer depends on K.
+  float* ysum = reinterpret_cast<float*>(smem + p.SA * stage_bytes);  // [P2_ROWS][ysum_ld]
+  double* dred = reinterpret_cast<double*>(smem + p.SA * stage_bytes + (size_t)P2_ROWS * p.ysum_ld * 4);
   uint64_t* bars = reinterpret_cast<uint64_t*>(dred + P2_RED_DOUBLES);
   uint64_t* full = bars;                   // [MAX_ST] TMA -> converters                      (local)
   uint64_t* empty = full + P2_MAX_ST;      // [MAX_ST] MMA commit (multicast) -> TMA           (local)
@@ -97,6 +105,7 @@ k_dense_stream2p(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t rank = cluster_ctarank();
   const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int nkb = (int)((p.K + BK - 1) / BK);
+  const int nseg = (nkb + p.seg - 1) / p.seg;
   const int G = p.G, MX = p.MX;
 
   if (warp == 0 && lane == 0) {
@@ -154,38 +163,42 @@ k_dense_stream2p(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (rank == 0) {
       int s = 0, sl = 0;
       uint32_t phl = 0, it = 0;
-      for (int64_t pt = pair; pt < p.nptiles; pt += npairs, ++it) {
-        const uint32_t buf = (p.acc_bufs == 2) ? (it & 1) : 0u;
-        const uint32_t accph = (p.acc_bufs == 2) ? ((it >> 1) & 1) : (it & 1);
-        mbar_wait(smem_u32(&acc_empty[buf]), accph ^ 1);
-        const uint32_t d0 = tmem_base + buf * 2 * p.acc_stride;
-        for (int kb = 0; kb < nkb; ++kb) {
-          // the converters of a CTA pass its full[s] before they arrive here: lo_full also says "both tiles have landed"
-          mbar_wait(smem_u32(&lo_full[sl]), phl);
-          __syncwarp();
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a_addr = smem_u32(sRing + s * stage_bytes);
-            const uint64_t xdesc = make_kmajor_desc<BK>(a_addr + A_STAGE);
-            const uint32_t lo_slot = tmem_base + p.slot_base + sl * (2 * BK);
+      for (int64_t pt = pair; pt < p.nptiles; pt += npairs) {
+        for (int kb0 = 0; kb0 < nkb; kb0 += p.seg, ++it) {  // one accumulator buffer per segment
+          const int kb1 = min(nkb, kb0 + p.seg);
+          const uint32_t buf = (p.acc_bufs == 2) ? (it & 1) : 0u;
+          const uint32_t accph = (p.acc_bufs == 2) ? ((it >> 1) & 1) : (it & 1);
+          mbar_wait(smem_u32(&acc_empty[buf]), accph ^ 1);
+          const uint32_t d0 = tmem_base + buf * 2 * p.acc_stride;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            // the converters of a CTA pass its full[s] before they arrive here: lo_full also says "both tiles landed"
+            mbar_wait(smem_u32(&lo_full[sl]), phl);
+            __syncwarp();
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_addr = smem_u32(sRing + s * stage_bytes);
+              const uint64_t xdesc = make_kmajor_desc<BK>(a_addr + A_STAGE);
+              const uint32_t lo_slot = tmem_base + p.slot_base + sl * (2 * BK);
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const uint64_t adesc = make_kmajor_desc<BK>(a_addr + t * (128 * ROW_BYTES));
-              const uint32_t d_addr = d0 + t * p.acc_stride;
+              for (int t = 0; t < 2; ++t) {
+                const uint64_t adesc = make_kmajor_desc<BK>(a_addr + t * (128 * ROW_BYTES));
+                const uint32_t d_addr = d0 + t * p.acc_stride;
 #pragma unroll
-              for (int k = 0; k < BK / 8; ++k) {
-                const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 8 tf32 = 32 bytes inside the swizzle span
-                if (!(p.dbg & 4)) umma_tf32_ss_pair(d_addr, adesc + adv, xdesc + adv, p.idesc_hi, (kb | k) ? 1u : 0u);
-                if (!(p.dbg & 5)) umma_tf32_ts_pair(d_addr, lo_slot + t * BK + k * 8, xdesc + adv, p.idesc_lo, 1u);
+                for (int k = 0; k < BK / 8; ++k) {
+                  const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 8 tf32 = 32 bytes inside the swizzle span
+                  if (!(p.dbg & 4))
+                    umma_tf32_ss_pair(d_addr, adesc + adv, xdesc + adv, p.idesc_hi, ((kb - kb0) | k) ? 1u : 0u);
+                  if (!(p.dbg & 5)) umma_tf32_ts_pair(d_addr, lo_slot + t * BK + k * 8, xdesc + adv, p.idesc_lo, 1u);
+                }
               }
+              umma_commit_pair(smem_u32(&empty[s]));
+              umma_commit_pair(smem_u32(&lo_empty[sl]));
+              if (kb == kb1 - 1) umma_commit_pair(smem_u32(&acc_full[buf]));
             }
-            umma_commit_pair(smem_u32(&empty[s]));
-            umma_commit_pair(smem_u32(&lo_empty[sl]));
-            if (kb == nkb - 1) umma_commit_pair(smem_u32(&acc_full[buf]));
+            __syncwarp();
+            if (++s == p.SA) s = 0;
+            if (++sl == NSLOT) { sl = 0; phl ^= 1; }
           }
-          __syncwarp();
-          if (++s == p.SA) s = 0;
-          if (++sl == NSLOT) { sl = 0; phl ^= 1; }
         }
       }
     }
@@ -196,81 +209,99 @@ k_dense_stream2p(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool need_e = (p.dg != nullptr) || (p.dots != nullptr);
     const int et = threadIdx.x - 128;  // 0..127 inside the epilogue group
     const uint32_t acc_empty_leader = map_to_cta(smem_u32(&acc_empty[0]), 0);
-    uint32_t it = 0;
-    for (int64_t pt = pair; pt < p.nptiles; pt += npairs, ++it) {
-      const uint32_t buf = (p.acc_bufs == 2) ? (it & 1) : 0u;
-      const uint32_t accph = (p.acc_bufs == 2) ? ((it >> 1) & 1) : (it & 1);
+    uint32_t it = 0, tile_no = 0;
+    for (int64_t pt = pair; pt < p.nptiles; pt += npairs, ++tile_no) {
       const int64_t b = pt / p.MTP;
       const int mt = (int)(pt - b * p.MTP) * 2 + (int)rank;
       const int64_t m0 = (int64_t)mt * P2_ROWS;
       const float alpha_b = p.alpha ? p.alpha[b * p.alpha_bs] : 1.0f;
       const float* Eb = p.E + b * p.M * C;
       float* Yb = p.Y + b * p.M * C;
-      double* red = dred + (it & 1) * (2 * 4 * 48);
-      mbar_wait(smem_u32(&acc_full[buf]), accph);
-      __syncwarp();
-      tc_fence_after();
+      double* red = dred + (tile_no & 1) * (2 * 4 * 48);
 #pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        const int64_t row = m0 + t * 128 + q * 32 + lane;
-        const bool rok = row < p.M;
-        const float dv = (p.dg && rok) ? __ldg(p.dg + b * p.d_bs + row * p.d_st) : 0.f;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + t) * p.acc_stride;
+      for (int seg = 0; seg < nseg; ++seg, ++it) {
+        const bool first = seg == 0, last = seg == nseg - 1;
+        const uint32_t buf = (p.acc_bufs == 2) ? (it & 1) : 0u;
+        const uint32_t accph = (p.acc_bufs == 2) ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(smem_u32(&acc_full[buf]), accph);
+        __syncwarp();
+        tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < 2 * G + 2 * MX; c0 += 16) {
-          float e[16];
+        for (int t = 0; t < 2; ++t) {
+          const int64_t row = m0 + t * 128 + q * 32 + lane;
+          const bool rok = row < p.M;
+          const float dv = (p.dg && rok && last) ? __ldg(p.dg + b * p.d_bs + row * p.d_st) : 0.f;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + t) * p.acc_stride;
+          float* ys = ysum + (t * 128 + q * 32 + lane) * p.ysum_ld;  // this row's running sum (odd pitch: no conflicts)
+#pragma unroll 1
+          for (int c0 = 0; c0 < 2 * G + 2 * MX; c0 += 16) {
+            float e[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) e[i] = (need_e && rok && c0 + i < C) ? __ldg(Eb + row * C + c0 + i) : 0.f;
-          uint32_t hi[16], lo[16];
-          if (c0 < 2 * G) {
-            // two 8-column groups (G % 8 == 0: a group never straddles the halves); partner columns per the layout above
-            const int ca = c0, cb = c0 + 8;
-            DS_LD8(taddr + (ca < G ? ca : ca + MX), hi);
-            DS_LD8(taddr + (ca < G ? 3 * G + 2 * MX + ca : ca + MX + G), lo);
-            DS_LD8(taddr + (cb < G ? cb : cb + MX), (hi + 8));
-            DS_LD8(taddr + (cb < G ? 3 * G + 2 * MX + cb : cb + MX + G), (lo + 8));
-          } else {
-            // the extras: column 2 g + j sits at D[g + 2 j] (A_hi x_hi + A_lo x_hi) and D[g + 2 j + 1] (A_hi x_lo)
-            uint32_t v[8];
-            DS_LD8(taddr + G, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int i = 0; i < 16; ++i)
+              e[i] = (need_e && last && rok && c0 + i < C) ? __ldg(Eb + row * C + c0 + i) : 0.f;
+            uint32_t hi[16], lo[16];
+            if (c0 < 2 * G) {
+              // two 8-column groups (G % 8 == 0: a group never straddles the halves); partner columns per the layout
+              const int ca = c0, cb = c0 + 8;
+              DS_LD8(taddr + (ca < G ? ca : ca + MX), hi);
+              DS_LD8(taddr + (ca < G ? 3 * G + 2 * MX + ca : ca + MX + G), lo);
+              DS_LD8(taddr + (cb < G ? cb : cb + MX), (hi + 8));
+              DS_LD8(taddr + (cb < G ? 3 * G + 2 * MX + cb : cb + MX + G), (lo + 8));
+            } else {
+              // the extras: column 2 g + j sits at D[g + 2 j] (A_hi x_hi + A_lo x_hi) and D[g + 2 j + 1] (A_hi x_lo)
+              uint32_t v[8];
+              DS_LD8(taddr + G, v);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0u;
+              for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0u;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) hi[i] = v[2 * i], lo[i] = v[2 * i + 1];
-          }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          double pd[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float y = fmaf(dv, e[i], (__uint_as_float(hi[i]) + __uint_as_float(lo[i])) * alpha_b);
-            const bool ok = rok && c0 + i < C;
-            if (ok) Yb[row * C + c0 + i] = y;
-            pd[i] = ok ? (double)e[i] * (double)y : 0.0;
-          }
-          if (p.dots) {
-            // column sums over the 32 rows of this warp as a transpose-reduce (fixed tree: deterministic); see
-            // dense_stream2.cu
-#pragma unroll
-            for (int hh = 8, o = 16; hh >= 1; hh >>= 1, o >>= 1) {
-              const bool up = (lane & o) != 0;
-#pragma unroll
-              for (int j = 0; j < hh; ++j) {
-                const double send = up ? pd[j] : pd[j + hh];
-                const double keep = up ? pd[j + hh] : pd[j];
-                pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-              }
+              for (int i = 0; i < 4; ++i) hi[i] = v[2 * i], lo[i] = v[2 * i + 1];
             }
-            pd[0] += __shfl_xor_sync(0xffffffffu, pd[0], 1);
-            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            if ((lane & 1) == 0) red[(t * 4 + q) * 48 + c0 + col] = pd[0];
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              acc[i] = __uint_as_float(hi[i]) + __uint_as_float(lo[i]);
+              if (!first && c0 + i < C) acc[i] += ys[c0 + i];
+            }
+            if (!last) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < C) ys[c0 + i] = acc[i];
+              continue;
+            }
+            double pd[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float y = fmaf(dv, e[i], acc[i] * alpha_b);
+              const bool ok = rok && c0 + i < C;
+              if (ok) Yb[row * C + c0 + i] = y;
+              pd[i] = ok ? (double)e[i] * (double)y : 0.0;
+            }
+            if (p.dots) {
+              // column sums over the 32 rows of this warp as a transpose-reduce (fixed tree: deterministic); see
+              // dense_stream2.cu
+#pragma unroll
+              for (int hh = 8, o = 16; hh >= 1; hh >>= 1, o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int j = 0; j < hh; ++j) {
+                  const double send = up ? pd[j] : pd[j + hh];
+                  const double keep = up ? pd[j + hh] : pd[j];
+                  pd[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+              }
+              pd[0] += __shfl_xor_sync(0xffffffffu, pd[0], 1);
+              const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+              if ((lane & 1) == 0) red[(t * 4 + q) * 48 + c0 + col] = pd[0];
+            }
           }
         }
+        // accumulators drained: hand the TMEM buffer of this CTA back to the leader's MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader + buf * 8);
       }
-      // accumulators drained: hand the TMEM buffer of this CTA back to the leader's MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(acc_empty_leader + buf * 8);
       if (p.dots) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int idx = et; idx < 2 * C; idx += 128) {
@@ -509,10 +540,15 @@ int dense_matmul_stream2p_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, co
   const int a_stage = P2_ROWS * BK * 4;
   const int xbytes = (int)align_up((size_t)R * BK * 4, 1024);
   const int stage = a_stage + xbytes;
-  int sa = cfg.sa > 0 ? cfg.sa : (int)((P2_SMEM_MAX - P2_SMEM_FIXED) / stage);
+  // accumulator segments of 64 k blocks (2048 contraction indices); one segment needs no running-sum tile
+  const int nkb_host = (int)cdiv(K, BK);
+  const int seg = (cfg.dbg & 4096) ? (1 << 30) : 64;
+  const int ysum_ld = nkb_host > seg ? ((int)C | 1) : 0;
+  const size_t ysum_bytes = align_up((size_t)P2_ROWS * ysum_ld * 4, 16);
+  int sa = cfg.sa > 0 ? cfg.sa : (int)((P2_SMEM_MAX - P2_SMEM_FIXED - ysum_bytes) / stage);
   if (sa > P2_MAX_ST) sa = P2_MAX_ST;
   if (sa < 2) return LOB_ERR_UNSUPPORTED;
-  const size_t smem = P2_SMEM_FIXED + (size_t)sa * stage;
+  const size_t smem = P2_SMEM_FIXED + (size_t)sa * stage + ysum_bytes;
   if (smem > P2_SMEM_MAX) return LOB_ERR_UNSUPPORTED;
 
   P2Params p;
@@ -539,6 +575,8 @@ int dense_matmul_stream2p_f32_cfg(int64_t B, int64_t M, int64_t K, int64_t C, co
   p.idesc_hi = ds::make_idesc_tf32(256, 2 * R);                  // either CTA supplies its R rows
   p.idesc_lo = ds::make_idesc_tf32(256, 2 * (lay.g + lay.mx));   // ... resp. its first g + mx rows
   p.dbg = cfg.dbg;
+  p.seg = seg;
+  p.ysum_ld = ysum_ld;
   p.acc_bufs = (cfg.acc_bufs == 1) ? 1 : 2;
   p.acc_stride = 2 * R;
   p.slot_base = 2 * p.acc_bufs * p.acc_stride;

@@ -134,7 +134,9 @@ def test_dense_matmul_generalised_epilogue(dtype, constant_diag, impl):
 @pytest.mark.parametrize("kernel", ["stream2p", "stream2"])
 def test_dense_stream_accumulation_bias_on_positive_data(kernel):
     """Worst case for the tensor core's truncating fp32 accumulate: all-positive operands, no cancellation.  The bias is
-    linear in K (measured 1.5e-8 * K relative); this pins it below the 1e-4 parity bar at N = 5000 and documents it."""
+    linear in the number of indices ONE accumulator sees (measured 1.5e-8 per index): 7.5e-5 at K = 5000 for the
+    single-CTA kernel, 2.5e-5 -- one 2048-index segment -- for the pair kernel, which drains its accumulator into a
+    round-to-nearest running sum every 64 k blocks.  Both are pinned below the 1e-4 parity bar."""
     _lib.pin_dense_impl(kernel)
     try:
         g = torch.Generator(device=DEV).manual_seed(11)
@@ -146,7 +148,7 @@ def test_dense_stream_accumulation_bias_on_positive_data(kernel):
     ref = A.double() @ X.double()
     rel = ((Y.double() - ref).abs() / ref.abs()).max().item()
     print(f"all-positive K=5000: rel err {rel:.3e}")
-    assert rel < 1e-4
+    assert rel < (4e-5 if kernel == "stream2p" else 1e-4)
     assert (Y.double() <= ref * (1 + 1e-6)).all()  # truncation only ever loses magnitude
 
 
