@@ -74,7 +74,11 @@ def dense_matmul(A: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = N
     dd, d_bs, d_st = _diag_args(d, batch_shape, M)
     dots = None
     n_parts = int(lib.lob_dense_matmul_parts(M))
-    if want_dots:
+    # small fp64 problems (BASELINE config 1) take a row-per-warp kernel without fused <X, Y> partial sums
+    # (csrc/matmul_simt.cu, k_matmul_rows: same rule there); linear_cg then adds its own dot pass
+    fused_dots = not (X.dtype == torch.float64 and B * M <= 8192 and K <= 8192 and C <= 64 and E is None
+                      and alpha is None)
+    if want_dots and fused_dots:
         dots = torch.empty(B, n_parts, C, dtype=torch.float64, device=X.device)
     # scratch of the streaming tensor-core kernel (tf32 split of X^T); torch's caching allocator makes this free
     ws_bytes = int(lib.lob_dense_matmul_workspace_bytes(dt(X), B, M, K, C))
@@ -103,7 +107,7 @@ def dense_matmul(A: torch.Tensor, X: torch.Tensor, d: Optional[torch.Tensor] = N
         prof.append((e0, e1, M == K))  # square = the operator matmul itself
     Y = Y.reshape(*batch_shape, M, C)
     if want_dots:
-        return Y, dots, n_parts
+        return Y, dots, (n_parts if dots is not None else 0)
     return Y
 
 

@@ -129,6 +129,58 @@ k_matmul_nn(int64_t M, int64_t K, int64_t C, const T* __restrict__ A, int64_t ld
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// Small fp64 problems (BASELINE config 1: N = 512, 17 columns, batch 1): the tiled kernel above gives such a product 4 CTAs
+// and 32 single-buffered k tiles, ~100 us of exposed latency per product and 78 % of the whole call.  Here a warp owns
+// one output row: lanes split the contraction (coalesced reads of the A row, X through L1), eight columns at a time in
+// registers, one shuffle reduction per column.  No fused <X, Y> partial sums (linear_cg adds its own dot pass).
+// ----------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_matmul_rows(int64_t M, int64_t K, int64_t C, const T* __restrict__ A, int64_t lda, int64_t a_bs, const T* __restrict__ X,
+              int64_t x_bs, T* __restrict__ Y, const T* __restrict__ dg, int64_t d_bs, int64_t d_st) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = blockIdx.y;
+  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+  if (row >= M) return;
+  const T* Ar = A + b * a_bs + row * lda;
+  const T* Xb = X + b * x_bs;
+  T* Yr = Y + (b * M + row) * C;
+  for (int64_t c0 = 0; c0 < C; c0 += 8) {
+    const int nc = (int)min((int64_t)8, C - c0);
+    T acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = (T)0;
+    for (int64_t k = lane; k < K; k += 32) {
+      const T a = Ar[k];
+      const T* xk = Xb + k * C + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nc) acc[j] += a * xk[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      T v = acc[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[j] = v;
+    }
+    if (lane < nc) {
+      T y = acc[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j)
+        if (lane == j) y = acc[j];
+      if (dg) y += dg[b * d_bs + row * d_st] * Xb[row * C + c0 + lane];  // square operator: E = X
+      Yr[c0 + lane] = y;
+    }
+  }
+}
+
+template <typename T>
+static bool rows_kernel_applies(int64_t B, int64_t M, int64_t K, int64_t C) {
+  return sizeof(T) == 8 && B * M <= 8192 && K <= 8192 && C <= 64;
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // Out partial (b, split, I, J) = sum_{n in split} P[n, i] Q[n, j]
 template <typename T, typename ACC, int RN>
 __global__ void __launch_bounds__(256)
@@ -201,6 +253,11 @@ template <typename T>
 static int launch_nn(int64_t B, int64_t M, int64_t K, int64_t C, const T* A, int64_t lda, int64_t a_bs, const T* X,
                      int64_t x_bs, T* Y, const T* d, int64_t d_bs, int64_t d_st, double* dots, double beta_y,
                      cudaStream_t st, const T* E = nullptr, const T* alpha = nullptr, int64_t alpha_bs = 0) {
+  if (!dots && !E && !alpha && beta_y == 0.0 && rows_kernel_applies<T>(B, M, K, C)) {
+    k_matmul_rows<T><<<dim3((unsigned)cdiv(M, 8), (unsigned)B), 256, 0, st>>>(M, K, C, A, lda, a_bs, X, x_bs, Y, d, d_bs,
+                                                                             d_st);
+    return check_launch("k_matmul_rows");
+  }
   const int rn = pick_rn(C);
   const int cp = 8 * rn;
   dim3 grid((unsigned)cdiv(M, TM), (unsigned)B, (unsigned)cdiv(C, cp));

@@ -131,6 +131,22 @@ def test_dense_matmul_generalised_epilogue(dtype, constant_diag, impl):
     assert ((T2.double() - ref2).abs().max() / ref2.abs().max()).item() < tol
 
 
+@pytest.mark.parametrize("B,N,C", [(1, 512, 17), (3, 500, 33), (2, 100, 5), (1, 1000, 64)])
+def test_dense_matmul_small_fp64_row_kernel(B, N, C):
+    """Small fp64 problems (BASELINE config 1) take the row-per-warp kernel: no fused <X, Y> partial sums (linear_cg adds
+    its own dot pass), fused + d (.) X, operator shared across the batch."""
+    g = torch.Generator(device=DEV).manual_seed(B + N + C)
+    A = torch.randn(B, N, N, device=DEV, generator=g, dtype=torch.float64) / N**0.5
+    X = torch.randn(B, N, C, device=DEV, generator=g, dtype=torch.float64)
+    d = 0.1 + torch.rand(B, N, device=DEV, generator=g, dtype=torch.float64)
+    Y, dots, n_parts = _kernels.dense_matmul(A, X, d=d, want_dots=True)
+    assert dots is None and n_parts == 0
+    ref = A @ X + d.unsqueeze(-1) * X
+    assert ((Y - ref).abs().max() / ref.abs().max()).item() < 1e-13
+    Y1 = _kernels.dense_matmul(A[:1], X)  # one operator for every batch element, no diagonal
+    assert ((Y1 - A[:1] @ X).abs().max() / ref.abs().max()).item() < 1e-13
+
+
 @pytest.mark.parametrize("kernel", ["stream2p", "stream2"])
 def test_dense_stream_accumulation_bias_on_positive_data(kernel):
     """Worst case for the tensor core's truncating fp32 accumulate: all-positive operands, no cancellation.  The bias is
