@@ -4,7 +4,10 @@
 // and loops over probes in Python; here one thread owns one tridiagonal (S*B of them, e.g. 32768 for BASELINE
 // config 2), runs the implicit-shift QL iteration in double precision and keeps only the first eigenvector row
 // unless the caller asks for the full eigenvector matrices.  Per-thread arrays live in a workspace laid out with
-// the matrix index fastest, so every access of a warp is coalesced.
+// the matrix index fastest, so every access of a warp is coalesced.  Small tridiagonals (T <= 48) keep d, e and the
+// first eigenvector row in shared memory instead (same layout, thread index fastest): the QL iteration is one long
+// dependent chain, and with a handful of matrices (16 at BASELINE config 1) every workspace access was an exposed L2
+// round trip -- 256 us for sixteen 20 x 20 problems.
 #include "common.cuh"
 
 namespace lob {
@@ -16,13 +19,19 @@ template <typename T>
 __global__ void k_tridiag_eig(int64_t nmat, int Tn, const T* __restrict__ t_mat, T* __restrict__ evals,
                               T* __restrict__ evecs, double* __restrict__ quad, int32_t* __restrict__ info,
                               double* __restrict__ wd, double* __restrict__ we, double* __restrict__ wz0,
-                              double* __restrict__ wz) {
+                              double* __restrict__ wz, int use_smem) {
+  extern __shared__ double tri_smem[];  // use_smem: [3][Tn][blockDim.x]
   const int64_t mat = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (mat >= nmat) return;
   const T* t = t_mat + mat * Tn * Tn;
-#define D(i) wd[(int64_t)(i) * nmat + mat]
-#define E(i) we[(int64_t)(i) * nmat + mat]
-#define Z0(i) wz0[(int64_t)(i) * nmat + mat]
+  const int64_t st_ = use_smem ? (int64_t)blockDim.x : nmat;  // distance between consecutive elements of one matrix
+  const int64_t ix_ = use_smem ? (int64_t)threadIdx.x : mat;
+  double* pd = use_smem ? tri_smem : wd;
+  double* pe = use_smem ? tri_smem + (size_t)Tn * blockDim.x : we;
+  double* pz0 = use_smem ? tri_smem + 2 * (size_t)Tn * blockDim.x : wz0;
+#define D(i) pd[(int64_t)(i) * st_ + ix_]
+#define E(i) pe[(int64_t)(i) * st_ + ix_]
+#define Z0(i) pz0[(int64_t)(i) * st_ + ix_]
 #define Z(r, c) wz[((int64_t)(r) * Tn + (c)) * nmat + mat]
   const int n = Tn;
   for (int i = 0; i < n; ++i) {
@@ -167,9 +176,13 @@ extern "C" int lob_tridiag_eigh_slq(int32_t dtype, int64_t S, int64_t B, int32_t
   double* wz = evecs ? wz0 + nmat * T : nullptr;
   LOB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
   LOB_DISPATCH_DTYPE(dtype, {
-    k_tridiag_eig<scalar_t><<<(unsigned)cdiv(nmat, 128), 128, 0, st>>>(nmat, T, (const scalar_t*)t_mat,
-                                                                       (scalar_t*)evals, (scalar_t*)evecs, quad, info,
-                                                                       wd, we, wz0, wz);
+    const int use_smem = T <= 48;
+    const int threads = use_smem ? 64 : 128;
+    const size_t smem = use_smem ? sizeof(double) * 3 * (size_t)T * threads : 0;
+    if (smem > 48 * 1024)
+      LOB_CUDA(cudaFuncSetAttribute(k_tridiag_eig<scalar_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tridiag_eig<scalar_t><<<(unsigned)cdiv(nmat, threads), threads, smem, st>>>(
+        nmat, T, (const scalar_t*)t_mat, (scalar_t*)evals, (scalar_t*)evecs, quad, info, wd, we, wz0, wz, use_smem);
     LOB_TRY(check_launch("k_tridiag_eig"));
     if (logdet) {
       k_slq_reduce<scalar_t><<<(unsigned)cdiv(B, 256), 256, 0, st>>>(S, B, (double)n / (double)S, quad,
