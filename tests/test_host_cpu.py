@@ -64,6 +64,9 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert lib.lob_lanczos_init(0, 0, 8, 1, None, None, None) == -1
     # streaming matmul scratch: (B, 2 * round_up(C, 8), K) floats for fp32, none for fp64 or C > 64
     assert lib.lob_dense_matmul_workspace_bytes(0, 1024, 5000, 5000, 33) == 1024 * 80 * 5000 * 4  # pair kernel: 2 x (2 g + 8) rows, g = 16
+    # operand rows of the pair kernel per column count: 2 x (2 g + 8) when C = 2 g + e with e <= 4, else 4 x ceil8(C / 2)
+    for C, rows in ((1, 32), (16, 32), (17, 48), (20, 48), (21, 64), (32, 64), (33, 80), (36, 80), (37, 96), (48, 96)):
+        assert lib.lob_dense_matmul_workspace_bytes(0, 2, 1000, 1000, C) >= 2 * rows * 1000 * 4, C
     assert lib.lob_dense_matmul_workspace_bytes(1, 1024, 5000, 5000, 33) == 0
     assert lib.lob_dense_matmul_workspace_bytes(0, 2, 100, 100, 65) == 0
     # Toeplitz column-pair path: sizes and NULL pointers are rejected before anything is launched
